@@ -1,0 +1,118 @@
+"""ctypes binding of the C ABI declared in include/msda_b200.h.
+
+The product path has NO fallback: if ``libmsda_b200.so`` is missing or does not load, importing the
+operator raises.  (The CPU oracle under oracle/ is test infrastructure and is never imported from here.)
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import shutil
+import subprocess
+
+_PKG = os.path.dirname(os.path.abspath(__file__))
+ROOT = os.path.dirname(_PKG)
+LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
+CSRC = os.path.join(_PKG, "csrc")
+HEADER = os.path.join(ROOT, "include", "msda_b200.h")
+
+ABI_VERSION = 1
+F32, BF16, F16, F64 = 0, 1, 2, 3
+
+NVCC_FLAGS = [
+    "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
+    "-Xcompiler", "-fPIC", "-shared",
+]
+
+
+class MsdaDims(ctypes.Structure):
+    """struct msda_dims (include/msda_b200.h)."""
+
+    _fields_ = [(n, ctypes.c_int) for n in
+                ("batch", "spatial_size", "num_heads", "channels", "num_levels", "num_query", "num_point")]
+
+
+def sources():
+    return [os.path.join(CSRC, "msda_capi.cu")]
+
+
+def needs_build() -> bool:
+    if not os.path.exists(LIB_PATH):
+        return True
+    t = os.path.getmtime(LIB_PATH)
+    deps = sources() + [os.path.join(CSRC, "msda_kernels.cuh"), HEADER]
+    return any(os.path.getmtime(d) > t for d in deps)
+
+
+def build_library(force: bool = False, verbose: bool = False) -> str:
+    """Compile the CUDA sources for sm_100a into the in-tree shared library (nvcc cross-compiles without a GPU)."""
+    if not force and not needs_build():
+        return LIB_PATH
+    nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
+    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    if verbose:
+        print(res.stderr)
+    return LIB_PATH
+
+
+_lib = None
+
+
+def lib() -> ctypes.CDLL:
+    """The loaded C-ABI library; raises (never falls back) if it is unavailable."""
+    global _lib
+    if _lib is not None:
+        return _lib
+    if not os.path.exists(LIB_PATH):
+        raise RuntimeError(
+            f"{LIB_PATH} not found: the sm_100a extension has not been built. "
+            "Run `python -c 'import __graft_entry__ as g; g.build()'` (needs nvcc). There is no CPU fallback."
+        )
+    L = ctypes.CDLL(LIB_PATH)
+    vp, i, sz = ctypes.c_void_p, ctypes.c_int, ctypes.c_size_t
+    dp = ctypes.POINTER(MsdaDims)
+    L.msda_version.restype = i
+    L.msda_version.argtypes = []
+    L.msda_last_error_string.restype = ctypes.c_char_p
+    L.msda_last_error_string.argtypes = []
+    L.msda_forward.restype = i
+    L.msda_forward.argtypes = [vp] * 6 + [dp, i, vp]
+    L.msda_forward_host.restype = i
+    L.msda_forward_host.argtypes = [vp] * 6 + [dp, i, vp]
+    L.msda_backward_workspace_bytes.restype = sz
+    L.msda_backward_workspace_bytes.argtypes = [dp, i]
+    L.msda_backward.restype = i
+    L.msda_backward.argtypes = [vp] * 10 + [sz, dp, i, i, vp]
+    L.msda_set_tuning.restype = i
+    L.msda_set_tuning.argtypes = [ctypes.c_char_p, i]
+    L.msda_get_tuning.restype = i
+    L.msda_get_tuning.argtypes = [ctypes.c_char_p, ctypes.POINTER(i)]
+    L.msda_kernel_launch_count.restype = ctypes.c_uint64
+    L.msda_kernel_launch_count.argtypes = []
+    if L.msda_version() != ABI_VERSION:
+        raise RuntimeError(f"libmsda_b200.so ABI {L.msda_version()} != binding ABI {ABI_VERSION}: rebuild")
+    _lib = L
+    return L
+
+
+def last_error() -> str:
+    return lib().msda_last_error_string().decode("utf-8", "replace")
+
+
+def set_tuning(name: str, value: int) -> None:
+    if lib().msda_set_tuning(name.encode(), int(value)) != 0:
+        raise ValueError(last_error())
+
+
+def get_tuning(name: str) -> int:
+    v = ctypes.c_int(0)
+    if lib().msda_get_tuning(name.encode(), ctypes.byref(v)) != 0:
+        raise ValueError(last_error())
+    return v.value
+
+
+def kernel_launch_count() -> int:
+    return int(lib().msda_kernel_launch_count())

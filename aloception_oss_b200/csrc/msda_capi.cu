@@ -1,0 +1,354 @@
+// msda_capi.cu -- C ABI (include/msda_b200.h) over the sm_100a kernels in msda_kernels.cuh.
+//
+// Host-side responsibilities mirror the reference launchers
+// (alonet/deformable_detr/ops/src/cuda/ms_deform_attn_cuda.cu:20-153 and
+//  ms_deform_im2col_cuda.cuh:923-954, 956-1327): validate, pick a kernel for (dtype, D), launch on the
+// caller's stream, report errors.  Unlike the reference there is no im2col_step batching loop (one launch
+// covers the whole batch with 64-bit indexing), no output memset in forward, and errors are returned
+// instead of printed.
+#include "../../include/msda_b200.h"
+
+#include <atomic>
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <type_traits>
+
+#include "msda_kernels.cuh"
+
+namespace {
+
+thread_local char g_err[512] = "";
+std::atomic<unsigned long long> g_launches{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0};
+
+int fail(const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return 1;
+}
+
+int check_launch(const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  const cudaError_t e = cudaPeekAtLastError();
+  if (e != cudaSuccess) {
+    cudaGetLastError();  // clear the (non-sticky) launch error
+    return fail("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
+size_t elt_size(int dtype) {
+  switch (dtype) {
+    case MSDA_F32: return 4;
+    case MSDA_BF16: case MSDA_F16: return 2;
+    case MSDA_F64: return 8;
+    default: return 0;
+  }
+}
+
+int validate_dims(const msda_dims* d, int dtype) {
+  if (!d) return fail("dims is NULL");
+  if (elt_size(dtype) == 0) return fail("unknown dtype %d (0=f32, 1=bf16, 2=f16, 3=f64)", dtype);
+  if (d->batch < 0 || d->spatial_size < 0 || d->num_heads < 0 || d->channels < 0 || d->num_levels < 0 ||
+      d->num_query < 0 || d->num_point < 0)
+    return fail("negative dimension in msda_dims");
+  if ((long long)d->num_levels * d->num_point > (1 << 20)) return fail("num_levels * num_point too large");
+  return 0;
+}
+
+bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
+
+struct Launch {
+  dim3 grid, block;
+};
+
+// one warp per (b, q, m) unit
+Launch unit_launch(long long units, int default_warps) {
+  int wpb = g_warps_per_block.load(std::memory_order_relaxed);
+  if (wpb <= 0 || wpb > MSDA_MAX_THREADS / 32) wpb = default_warps;
+  Launch l;
+  l.block = dim3(32 * wpb);
+  l.grid = dim3((unsigned)((units + wpb - 1) / wpb));
+  return l;
+}
+
+int pick_unroll(int knob, int fallback) {
+  const int u = knob;
+  return (u == 1 || u == 2 || u == 4) ? u : fallback;
+}
+
+// ---------------------------------------------------------------------------------------------
+// forward dispatch
+// ---------------------------------------------------------------------------------------------
+template <typename T, int D>
+int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
+                   void* out, const msda_dims& d, long long units, cudaStream_t st) {
+  const Launch l = unit_launch(units, 8);
+  const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 4);
+#define MSDA_FWD(UU)                                                                                          \
+  msda::msda_fwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
+      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
+      d.num_levels, d.num_query, d.num_point, 1.0f / (float)(d.num_point > 0 ? d.num_point : 1), units)
+  if (U == 1) MSDA_FWD(1); else if (U == 2) MSDA_FWD(2); else MSDA_FWD(4);
+#undef MSDA_FWD
+  return check_launch("msda_forward(vector)");
+}
+
+template <typename T>
+int launch_fwd_generic(const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                       const void* attn, void* out, const msda_dims& d, long long units, cudaStream_t st) {
+  const Launch l = unit_launch(units, 8);
+  msda::msda_fwd_generic_kernel<T><<<l.grid, l.block, 0, st>>>(
+      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,
+      d.channels, d.num_levels, d.num_query, d.num_point, units);
+  return check_launch("msda_forward(generic)");
+}
+
+template <typename T>
+int forward_typed(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
+                  void* out, const msda_dims& d, long long units, cudaStream_t st) {
+  const bool vec_ok = !g_force_generic.load(std::memory_order_relaxed) && d.num_levels <= 32 &&
+                      d.num_point < (1 << 15) && aligned(value, 16) && aligned(out, 16) &&
+                      aligned(loc, 2 * sizeof(T)) && aligned(attn, sizeof(T));
+  if (vec_ok) {
+    switch (d.channels) {
+      case 16: return launch_fwd_vec<T, 16>(value, shapes, start, loc, attn, out, d, units, st);
+      case 32: return launch_fwd_vec<T, 32>(value, shapes, start, loc, attn, out, d, units, st);
+      case 64: return launch_fwd_vec<T, 64>(value, shapes, start, loc, attn, out, d, units, st);
+      case 128: return launch_fwd_vec<T, 128>(value, shapes, start, loc, attn, out, d, units, st);
+      default: break;
+    }
+  }
+  return launch_fwd_generic<T>(value, shapes, start, loc, attn, out, d, units, st);
+}
+
+// ---------------------------------------------------------------------------------------------
+// backward dispatch
+// ---------------------------------------------------------------------------------------------
+int zero_fill(void* p, size_t bytes, cudaStream_t st) {
+  if (bytes == 0) return 0;
+  if (!aligned(p, 16)) {  // odd views: let the driver do it
+    const cudaError_t e = cudaMemsetAsync(p, 0, bytes, st);
+    return e == cudaSuccess ? 0 : fail("cudaMemsetAsync: %s", cudaGetErrorString(e));
+  }
+  const long long n16 = (long long)(bytes / 16);
+  const int ntail = (int)(bytes % 16);
+  long long blocks = (n16 + 256 * 4 - 1) / (256 * 4);  // ~4 stores per thread
+  if (blocks < 1) blocks = 1;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  msda::msda_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, ntail);
+  return check_launch("msda_backward(zero grad_value)");
+}
+
+template <typename T, int D>
+int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                   const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, long long units,
+                   cudaStream_t st) {
+  const Launch l = unit_launch(units, 8);
+  const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 2);
+#define MSDA_BWD(UU)                                                                                          \
+  msda::msda_bwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
+      (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, gv, (T*)gloc, (T*)gattn,    \
+      d.spatial_size, d.num_heads, d.num_levels, d.num_query, d.num_point,                                     \
+      1.0f / (float)(d.num_point > 0 ? d.num_point : 1), units)
+  if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4);
+#undef MSDA_BWD
+  return check_launch("msda_backward(vector)");
+}
+
+template <typename T>
+int backward_typed(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                   const void* attn, void* grad_value, void* gloc, void* gattn, void* workspace, const msda_dims& d,
+                   long long units, cudaStream_t st) {
+  using A = typename msda::AccOf<T>::type;
+  const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  constexpr bool needs_ws = sizeof(T) != sizeof(A);
+  A* acc = needs_ws ? (A*)workspace : (A*)grad_value;
+  if (int rc = zero_fill(acc, n_value * sizeof(A), st)) return rc;
+  if (units > 0 && d.channels > 0 && d.num_levels * d.num_point > 0) {
+    bool done = false;
+    if constexpr (!std::is_same<T, double>::value) {
+      const bool vec_ok = !g_force_generic.load(std::memory_order_relaxed) && d.num_levels <= 32 &&
+                          d.num_point < (1 << 15) && aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) && aligned(loc, 2 * sizeof(T)) &&
+                          aligned(gloc, sizeof(T)) && aligned(attn, sizeof(T));
+      if (vec_ok) {
+        int rc = -1;
+        switch (d.channels) {
+          case 16: rc = launch_bwd_vec<T, 16>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
+          case 32: rc = launch_bwd_vec<T, 32>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
+          case 64: rc = launch_bwd_vec<T, 64>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
+          case 128: rc = launch_bwd_vec<T, 128>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
+          default: break;
+        }
+        if (rc > 0) return rc;
+        done = rc == 0;
+      }
+    }
+    if (!done) {
+      const Launch l = unit_launch(units, 8);
+      msda::msda_bwd_generic_kernel<T><<<l.grid, l.block, 0, st>>>(
+          (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, acc, (T*)gloc, (T*)gattn,
+          d.spatial_size, d.num_heads, d.channels, d.num_levels, d.num_query, d.num_point, units);
+      if (int rc = check_launch("msda_backward(generic)")) return rc;
+    }
+  }
+  if constexpr (needs_ws) {
+    if (n_value > 0) {
+      long long blocks = (long long)((n_value + 256 * 8 - 1) / (256 * 8));
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      msda::msda_cvt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)acc, (T*)grad_value, (long long)n_value);
+      if (int rc = check_launch("msda_backward(convert grad_value)")) return rc;
+    }
+  }
+  return 0;
+}
+
+struct DeviceGuard {
+  // kernels launch on the device that owns `stream`'s context = the caller's current device; nothing to do.
+};
+
+}  // namespace
+
+extern "C" {
+
+int msda_version(void) { return MSDA_ABI_VERSION; }
+
+const char* msda_last_error_string(void) { return g_err; }
+
+uint64_t msda_kernel_launch_count(void) { return g_launches.load(std::memory_order_relaxed); }
+
+static std::atomic<int>* knob(const char* name) {
+  if (!name) return nullptr;
+  if (!strcmp(name, "force_generic")) return &g_force_generic;
+  if (!strcmp(name, "fwd_unroll")) return &g_fwd_unroll;
+  if (!strcmp(name, "bwd_unroll")) return &g_bwd_unroll;
+  if (!strcmp(name, "warps_per_block")) return &g_warps_per_block;
+  return nullptr;
+}
+
+int msda_set_tuning(const char* name, int value) {
+  std::atomic<int>* k = knob(name);
+  if (!k) return fail("unknown tuning knob '%s'", name ? name : "(null)");
+  k->store(value, std::memory_order_relaxed);
+  return 0;
+}
+
+int msda_get_tuning(const char* name, int* value) {
+  std::atomic<int>* k = knob(name);
+  if (!k || !value) return fail("unknown tuning knob '%s'", name ? name : "(null)");
+  *value = k->load(std::memory_order_relaxed);
+  return 0;
+}
+
+int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims, int dtype,
+                 void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate_dims(dims, dtype)) return rc;
+  const msda_dims& d = *dims;
+  const long long units = (long long)d.batch * d.num_query * d.num_heads;
+  if (units == 0 || d.channels == 0) return 0;  // empty output
+  if (!output) return fail("output is NULL");
+  const bool has_samples = d.num_levels > 0 && d.num_point > 0;
+  if (has_samples && (!value || !spatial_shapes || !level_start_index || !sampling_loc || !attn_weight))
+    return fail("NULL tensor pointer passed to msda_forward");
+  if ((units + 7) / 8 > 0x7fffffffLL) return fail("problem too large for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case MSDA_F32: return forward_typed<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+    case MSDA_BF16: return forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+    case MSDA_F16: return forward_typed<__half>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+    case MSDA_F64: return launch_fwd_generic<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+  }
+  return fail("unreachable");
+}
+
+size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype) {
+  if (!dims) return 0;
+  if (dtype == MSDA_BF16 || dtype == MSDA_F16)
+    return sizeof(float) * (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+  return 0;
+}
+
+int msda_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
+                  const int32_t* level_start_index, const void* sampling_loc, const void* attn_weight,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                  size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate_dims(dims, dtype)) return rc;
+  if (flags != 0) return fail("flags must be 0");
+  const msda_dims& d = *dims;
+  const long long units = (long long)d.batch * d.num_query * d.num_heads;
+  const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  const size_t need = msda_backward_workspace_bytes(dims, dtype);
+  if (need > 0 && n_value > 0 && (!workspace || workspace_bytes < need))
+    return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  if (n_value > 0 && !grad_value) return fail("grad_value is NULL");
+  const bool has_samples = units > 0 && d.num_levels > 0 && d.num_point > 0;
+  if (has_samples && (!grad_output || !value || !spatial_shapes || !level_start_index || !sampling_loc ||
+                      !attn_weight || !grad_sampling_loc || !grad_attn_weight))
+    return fail("NULL tensor pointer passed to msda_backward");
+  if ((units + 7) / 8 > 0x7fffffffLL) return fail("problem too large for one launch");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case MSDA_F32: return backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_BF16: return backward_typed<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_F16: return backward_typed<__half>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_F64: return backward_typed<double>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+  }
+  return fail("unreachable");
+}
+
+int msda_forward_host(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                      const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims, int dtype,
+                      void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate_dims(dims, dtype)) return rc;
+  const msda_dims& d = *dims;
+  const size_t e = elt_size(dtype);
+  const size_t b_value = e * (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  const size_t b_attn = e * (size_t)d.batch * d.num_query * d.num_heads * d.num_levels * d.num_point;
+  const size_t b_loc = 2 * b_attn;
+  const size_t b_out = e * (size_t)d.batch * d.num_query * d.num_heads * d.channels;
+  const size_t b_shapes = sizeof(int32_t) * 2 * (size_t)d.num_levels, b_start = sizeof(int32_t) * (size_t)d.num_levels;
+  if (b_out == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  auto up = [](size_t x) { return (x + 255) & ~(size_t)255; };
+  const size_t o_value = 0, o_loc = o_value + up(b_value), o_attn = o_loc + up(b_loc), o_out = o_attn + up(b_attn),
+               o_shapes = o_out + up(b_out), o_start = o_shapes + up(b_shapes), total = o_start + up(b_start);
+  char* dev = nullptr;
+  cudaError_t ce = cudaMallocAsync((void**)&dev, total, st);
+  if (ce != cudaSuccess) return fail("cudaMallocAsync(%zu): %s", total, cudaGetErrorString(ce));
+  int rc = 0;
+  auto h2d = [&](size_t off, const void* src, size_t n) {
+    if (rc == 0 && n > 0) {
+      if (!src) { rc = fail("NULL host pointer passed to msda_forward_host"); return; }
+      const cudaError_t c = cudaMemcpyAsync(dev + off, src, n, cudaMemcpyHostToDevice, st);
+      if (c != cudaSuccess) rc = fail("cudaMemcpyAsync H2D: %s", cudaGetErrorString(c));
+    }
+  };
+  h2d(o_value, value, b_value);
+  h2d(o_loc, sampling_loc, b_loc);
+  h2d(o_attn, attn_weight, b_attn);
+  h2d(o_shapes, spatial_shapes, b_shapes);
+  h2d(o_start, level_start_index, b_start);
+  if (rc == 0)
+    rc = msda_forward(dev + o_value, (const int32_t*)(dev + o_shapes), (const int32_t*)(dev + o_start), dev + o_loc,
+                      dev + o_attn, dev + o_out, dims, dtype, stream);
+  if (rc == 0) {
+    if (!output) rc = fail("output is NULL");
+    else {
+      const cudaError_t c = cudaMemcpyAsync(output, dev + o_out, b_out, cudaMemcpyDeviceToHost, st);
+      if (c != cudaSuccess) rc = fail("cudaMemcpyAsync D2H: %s", cudaGetErrorString(c));
+    }
+  }
+  cudaFreeAsync(dev, st);
+  const cudaError_t se = cudaStreamSynchronize(st);
+  if (rc == 0 && se != cudaSuccess) rc = fail("stream synchronize: %s", cudaGetErrorString(se));
+  return rc;
+}
+
+}  // extern "C"

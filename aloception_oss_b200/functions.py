@@ -1,0 +1,193 @@
+"""Host side of the operator: mirror of ``alonet/deformable_detr/ops/functions``.
+
+Same names, argument meaning and error behaviour as the reference
+(alonet/deformable_detr/ops/functions/ms_deform_attn_func.py and ops/functions/__init__.py:9-14):
+
+* ``MSDeformAttnFunction``                      <- ms_deform_attn_func.py:49-82
+* ``load_MultiScaleDeformableAttention``        <- ms_deform_attn_func.py:29-46 (here: register the torch ops, never shells out)
+* ``load_ops``                                  <- ms_deform_attn_func.py:22-26
+* ``ms_deform_attn_core_pytorch``               <- ms_deform_attn_func.py:85-107 (tracing / export path only)
+* ``ms_deform_attn_forward`` / ``_backward``    <- the C++ entry points behind torch.ops.alonet_custom.*
+  (ops/src/ms_deform_attn.h:20-62, ops/src/cuda/ms_deform_attn_cuda.cu:20-153)
+
+The compute is done by the C-ABI library (include/msda_b200.h) through ctypes; torch supplies device
+memory and the current stream.  There is no CPU implementation: CPU tensors raise, as in the reference
+("Not implemented on the CPU", ops/src/ms_deform_attn.h:38,60).
+"""
+from __future__ import annotations
+
+import ctypes
+
+import torch
+import torch.nn.functional as F
+from torch.autograd import Function
+from torch.autograd.function import once_differentiable
+
+from . import _capi
+
+_DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16, torch.float64: _capi.F64}
+
+
+def _check_inputs(named):
+    # same order and wording as the AT_ASSERTM blocks of ms_deform_attn_cuda.cu:28-38 / :93-105
+    for name, t in named:
+        if not t.is_contiguous():
+            raise RuntimeError(f"{name} tensor has to be contiguous")
+    for name, t in named:
+        if not t.is_cuda:
+            raise RuntimeError(f"{name} must be a CUDA tensor")
+
+
+def _dims_of(value, spatial_shapes, sampling_loc, attn_weight):
+    if value.dim() != 4:
+        raise RuntimeError(f"value must be (N, S, M, D), got {tuple(value.shape)}")
+    if sampling_loc.dim() != 6 or sampling_loc.shape[-1] != 2:
+        raise RuntimeError(f"sampling_loc must be (N, Lq, M, L, P, 2), got {tuple(sampling_loc.shape)}")
+    N, S, M, D = value.shape
+    L = spatial_shapes.shape[0]
+    Lq, P = sampling_loc.shape[1], sampling_loc.shape[4]
+    if spatial_shapes.dim() != 2 or spatial_shapes.shape[1] != 2:
+        raise RuntimeError(f"spatial_shapes must be (L, 2), got {tuple(spatial_shapes.shape)}")
+    if tuple(sampling_loc.shape) != (N, Lq, M, L, P, 2):
+        raise RuntimeError(
+            f"sampling_loc {tuple(sampling_loc.shape)} inconsistent with value {tuple(value.shape)} and {L} levels")
+    if tuple(attn_weight.shape) != (N, Lq, M, L, P):
+        raise RuntimeError(f"attn_weight must be {(N, Lq, M, L, P)}, got {tuple(attn_weight.shape)}")
+    return _capi.MsdaDims(N, S, M, D, L, Lq, P)
+
+
+def _meta_i32(t, name):
+    if t.dtype == torch.int32:
+        return t
+    if t.dtype == torch.int64:  # upstream Deformable-DETR passes int64; this fork int32
+        return t.to(torch.int32)
+    raise RuntimeError(f"{name} must be an int32 (or int64) tensor, got {t.dtype}")
+
+
+def _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, extra=()):
+    _check_inputs([("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+                   ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra])
+    if value.dtype not in _DTYPES:
+        raise RuntimeError(f"ms_deform_attn: unsupported dtype {value.dtype} (float32, float64, bfloat16, float16)")
+    for name, t in (("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra):
+        if t.dtype != value.dtype:
+            raise RuntimeError(f"{name} has dtype {t.dtype}, expected {value.dtype} (same as value)")
+        if t.device != value.device:
+            raise RuntimeError(f"{name} is on {t.device}, value on {value.device}")
+    dims = _dims_of(value, spatial_shapes, sampling_loc, attn_weight)
+    if level_start_index.numel() != dims.num_levels:
+        raise RuntimeError("level_start_index must have one entry per level")
+    batch = dims.batch
+    step = min(batch, int(im2col_step))
+    # ms_deform_attn_cuda.cu:50-52 -- kept for API fidelity; the kernels themselves do not batch by im2col_step
+    if batch > 0 and (step <= 0 or batch % step != 0):
+        raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")
+    return dims
+
+
+def _ptr(t):
+    return ctypes.c_void_p(t.data_ptr()) if t.numel() else ctypes.c_void_p(0)
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
+    """CUDA forward: (N,S,M,D), (L,2) i32, (L,) i32, (N,Lq,M,L,P,2), (N,Lq,M,L,P) -> (N, Lq, M*D)."""
+    dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
+    shapes = _meta_i32(spatial_shapes, "spatial_shapes")
+    start = _meta_i32(level_start_index, "level_start_index")
+    out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _capi.lib().msda_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight),
+                                      _ptr(out), ctypes.byref(dims), _DTYPES[value.dtype], ctypes.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError("msda_forward failed: " + _capi.last_error())
+    return out
+
+
+def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
+                            im2col_step=64):
+    """CUDA backward -> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:83-153)."""
+    dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
+                          extra=(("grad_output", grad_output),))
+    if grad_output.numel() != dims.batch * dims.num_query * dims.num_heads * dims.channels:
+        raise RuntimeError(f"grad_output {tuple(grad_output.shape)} does not match the forward output")
+    shapes = _meta_i32(spatial_shapes, "spatial_shapes")
+    start = _meta_i32(level_start_index, "level_start_index")
+    grad_value = torch.empty_like(value)
+    grad_loc = torch.empty_like(sampling_loc)
+    grad_attn = torch.empty_like(attn_weight)
+    L = _capi.lib()
+    dt = _DTYPES[value.dtype]
+    ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = L.msda_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc),
+                             _ptr(attn_weight), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
+                             _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, ctypes.byref(dims), dt, 0,
+                             ctypes.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError("msda_backward failed: " + _capi.last_error())
+    return [grad_value, grad_loc, grad_attn]
+
+
+def load_ops():
+    """Reference: torch.ops.load_library(<build dir>/MultiScaleDeformableAttention.so).  Here: load the C-ABI
+    library and make sure ``torch.ops.alonet_custom.ms_deform_attn_{forward,backward}`` exist."""
+    from . import torch_ops
+
+    _capi.lib()
+    torch_ops.register()
+
+
+def load_MultiScaleDeformableAttention():
+    """Must be called once before using MSDeformAttnFunction (same contract as the reference); idempotent and
+    cheap.  Unlike the reference it never shells out to a build script: a missing library raises."""
+    load_ops()
+
+
+class MSDeformAttnFunction(Function):
+    """``apply(value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+    im2col_step)`` -> (N, Lq, M*D); gradients for arguments 0, 3 and 4 only."""
+
+    @staticmethod
+    def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                im2col_step):
+        ctx.im2col_step = im2col_step
+        output = torch.ops.alonet_custom.ms_deform_attn_forward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+            ctx.im2col_step)
+        ctx.save_for_backward(value, value_spatial_shapes, value_level_start_index, sampling_locations,
+                              attention_weights)
+        return output
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+        grad_value, grad_sampling_loc, grad_attn_weight = torch.ops.alonet_custom.ms_deform_attn_backward(
+            value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+            grad_output.contiguous(), ctx.im2col_step)
+        return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
+
+
+def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
+    """Pure-PyTorch formulation for tracing / ONNX / TensorRT export ONLY (the ``is_tracing`` branch of
+    ``MSDeformAttn.forward``, reference ops/modules/ms_deform_attn.py:138-144).  It is not a fallback of the CUDA
+    operator: nothing in this package routes to it unless the caller asks for the traceable graph.
+
+    Built on ``F.grid_sample(bilinear, zeros, align_corners=False)``, which is the same function as the
+    reference's hand-written ``bilinear_grid_sample`` (equal to 2e-9)."""
+    N, S, M, D = value.shape
+    _, Lq, _, L, P, _ = sampling_locations.shape
+    sizes = [(int(h), int(w)) for h, w in value_spatial_shapes]
+    levels = value.split([h * w for h, w in sizes], dim=1)
+    grids = 2 * sampling_locations - 1
+    per_level = []
+    for lvl, (h, w) in enumerate(sizes):
+        img = levels[lvl].flatten(2).transpose(1, 2).reshape(N * M, D, h, w)
+        grid = grids[:, :, :, lvl].transpose(1, 2).flatten(0, 1)
+        per_level.append(F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False))
+    weights = attention_weights.transpose(1, 2).reshape(N * M, 1, Lq, L * P)
+    out = (torch.stack(per_level, dim=-2).flatten(-2) * weights).sum(-1).view(N, M * D, Lq)
+    return out.transpose(1, 2).contiguous()

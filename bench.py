@@ -1,0 +1,452 @@
+#!/usr/bin/env python3
+"""bench.py -- headline benchmark of the B200 multi-scale deformable attention operator.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--workload C2] [--dtype f32]
+    python -m torch.distributed.run --nnodes=1 --nproc-per-node N --master-addr 127.0.0.1 --master-port P \
+        bench.py --gpus N --steps K --warmup W
+
+One "step" = one forward + one backward of the operator over one batch of synthetic input
+(BASELINE.json metric: "MSDeformAttn fwd+bwd Gsamples/s at COCO 4-level shapes"; sample = one (n, q, m, l, p)
+sampling point).  Default workload = BASELINE.json configs[1]/[2] ("C2": N=2 per GPU, levels 100/50/25/13 squared,
+300 queries, 8 heads, 4 points, d=256).  Multi-GPU = weak scaling: every rank owns its own batch shard, no
+collective on the data path; one NCCL broadcast of the level metadata at set-up.
+
+Prints ONE JSON line (rank 0).  See DESIGN.md "Measurement" for how every field is obtained.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import statistics
+import sys
+import threading
+import time
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+METRIC = "MSDeformAttn fwd+bwd Gsamples/s (COCO 4-level shapes)"
+UNIT = "Gsamples/s"
+L2_BYTES = 126 * 1024 * 1024
+FALLBACK_HBM_GBS = 6650.0  # /opt/skills/guides/B200_PROFILING.md fallback when MEASURED_PEAKS.json is absent
+
+
+def parse_args():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=2000)
+    ap.add_argument("--warmup", type=int, default=20)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--workload", default="C2")
+    ap.add_argument("--dtype", default="f32", choices=["f32", "bf16", "f16"])
+    ap.add_argument("--loc-mode", default="unit")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--extra", action="store_true", help="also time the other COCO shapes (reported under 'extra')")
+    return ap.parse_args()
+
+
+def hbm_peak():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    try:
+        with open(p) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    except Exception:
+        return FALLBACK_HBM_GBS, "fallback (B200_PROFILING.md 6.65 TB/s)"
+
+
+# ------------------------------------------------------------------------------------------------------------
+# clocks
+# ------------------------------------------------------------------------------------------------------------
+class ClockSampler:
+    """Samples SM clock + throttle reasons of one GPU through NVML every 20 ms while running."""
+
+    BAD = {"hw_slowdown": 0x8, "sw_thermal_slowdown": 0x20, "hw_thermal_slowdown": 0x40, "hw_power_brake": 0x80}
+    NOTE = {"sw_power_cap": 0x4, "sync_boost": 0x10, "display_clocks": 0x100}
+
+    def __init__(self, index):
+        self.index, self.samples, self.reasons, self.max_mhz = index, [], set(), None
+        self._stop = threading.Event()
+        self._thr = None
+        try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            self.nv = pynvml
+            self.h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = int(pynvml.nvmlDeviceGetMaxClockInfo(self.h, pynvml.NVML_CLOCK_SM))
+        except Exception:
+            self.nv = None
+
+    def _run(self):
+        nv = self.nv
+        while not self._stop.is_set():
+            try:
+                self.samples.append(int(nv.nvmlDeviceGetClockInfo(self.h, nv.NVML_CLOCK_SM)))
+                try:
+                    r = int(nv.nvmlDeviceGetCurrentClocksEventReasons(self.h))
+                except Exception:
+                    r = int(nv.nvmlDeviceGetCurrentClocksThrottleReasons(self.h))
+                for k, bit in {**self.BAD, **self.NOTE}.items():
+                    if r & bit:
+                        self.reasons.add(k)
+            except Exception:
+                pass
+            self._stop.wait(0.02)
+
+    def start(self):
+        if self.nv is not None:
+            self._thr = threading.Thread(target=self._run, daemon=True)
+            self._thr.start()
+        return self
+
+    def stop(self):
+        self._stop.set()
+        if self._thr is not None:
+            self._thr.join()
+        med = int(statistics.median(self.samples)) if self.samples else None
+        return {"sm_mhz": med, "sm_max_mhz": self.max_mhz, "reasons": sorted(self.reasons), "samples": len(self.samples)}
+
+
+# ------------------------------------------------------------------------------------------------------------
+# reference arm / cpu baseline: the reference's CPU implementation of the path (pure PyTorch), ported
+# ------------------------------------------------------------------------------------------------------------
+def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit"):
+    """Times forward + autograd backward of oracle/msda_torch_port.py on the host cores.
+
+    Returns (Gsamples/s, ms per step, steps run, sample description, threads)."""
+    import torch
+
+    from aloception_oss_b200.synthetic import Workload, torch_inputs
+    from oracle.msda_torch_port import msda_fwd_bwd_port
+
+    threads = os.cpu_count() or 1
+    torch.set_num_threads(threads)
+    w = workload
+    x = torch_inputs(w, seed=3, loc_mode=loc_mode)
+    t0 = time.perf_counter()
+    msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])  # warm-up + cost probe
+    probe = time.perf_counter() - t0
+    desc = f"{w.name}: full batch N={w.N}, Lq={w.Lq}"
+    if steps is not None and steps * probe > budget_s and w.Lq > 1:
+        # bound the run: keep the full value pyramid, take a prefix of the queries
+        lq = max(1, int(w.Lq * budget_s / (steps * probe)))
+        w = Workload(w.name, w.N, w.levels, lq, w.M, w.P, w.D)
+        x = dict(x, loc=x["loc"][:, :lq].contiguous(), attn=x["attn"][:, :lq].contiguous(),
+                 grad_out=x["grad_out"][:, :lq].contiguous())
+        desc = f"{workload.name}: N={w.N}, first {lq} of {workload.Lq} queries per image (bounded sample)"
+    n = steps if steps is not None else max(3, min(200, int(budget_s / max(probe, 1e-4))))
+    t0 = time.perf_counter()
+    for _ in range(n):
+        msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
+    dt = time.perf_counter() - t0
+    return w.samples * n / dt / 1e9, dt / n * 1e3, n, desc, threads
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from aloception_oss_b200.synthetic import WORKLOADS
+
+    w = WORKLOADS[args.workload]
+    for _ in range(max(0, min(args.warmup, 2))):
+        pass
+    rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=120.0, steps=args.steps, loc_mode=args.loc_mode)
+    line = {
+        "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
+        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": f"{w.name}: N={w.N}, levels={list(w.levels)}, Lq={w.Lq}, M={w.M}, P={w.P}, D={w.D}; "
+                               "fwd + autograd bwd of the reference's pure-PyTorch CPU path (port)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------
+# own arm
+# ------------------------------------------------------------------------------------------------------------
+def main():
+    args = parse_args()
+    if args.impl == "reference":
+        return run_reference(args)
+
+    import torch
+    import torch.distributed as dist
+
+    import aloception_oss_b200 as msda
+    from aloception_oss_b200 import _capi
+    from aloception_oss_b200.synthetic import WORKLOADS, device_inputs, level_tensors
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    torch.cuda.set_device(local)
+    dev = torch.device("cuda", local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    msda.load_ops()
+
+    tdt = {"f32": torch.float32, "bf16": torch.bfloat16, "f16": torch.float16}[args.dtype]
+    elt = 4 if args.dtype == "f32" else 2
+    w = WORKLOADS[args.workload]  # per-GPU shard (weak scaling)
+
+    # the only replicated state: level metadata, broadcast once from rank 0 (no collective on the data path)
+    shapes_np, start_np = level_tensors(w.levels)
+    meta = torch.from_numpy(shapes_np).to(dev).reshape(-1) if rank == 0 else torch.zeros(2 * w.L, dtype=torch.int32, device=dev)
+    if world > 1:
+        dist.broadcast(meta, src=0)
+    assert meta.cpu().tolist() == shapes_np.reshape(-1).tolist()
+
+    # rotating input sets: total footprint > 2x L2 so that every step reads its inputs from HBM
+    step_bytes = w.algorithmic_bytes(elt, False) + w.algorithmic_bytes(elt, True)
+    n_sets = max(4, int(2 * L2_BYTES / step_bytes) + 2)
+    while n_sets * step_bytes > 40e9 and n_sets > 2:
+        n_sets -= 1
+    sets = [device_inputs(w, seed=1000 * rank + i, device=dev, dtype=tdt, loc_mode=args.loc_mode) for i in range(n_sets)]
+
+    def fwd(s):
+        return msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
+
+    def bwd(s):
+        return msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
+
+    def step(i):
+        s = sets[i % n_sets]
+        return fwd(s), bwd(s)
+
+    K, W = args.steps, max(args.warmup, 3)
+    for i in range(W):
+        step(i)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def capture(fn, n):
+        """CUDA graph of n consecutive calls fn(i); returns (graph, launches recorded)."""
+        g = torch.cuda.CUDAGraph()
+        c0 = _capi.kernel_launch_count()
+        with torch.cuda.graph(g):
+            for i in range(n):
+                fn(i)
+        return g, _capi.kernel_launch_count() - c0
+
+    def time_graph(g, replays=1):
+        g.replay()  # untimed: graph upload / first-replay cost
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(replays):
+            g.replay()
+        e1.record()
+        barrier()
+        ms = e0.elapsed_time(e1)
+        if world > 1:
+            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            ms = float(t.item())
+        return ms
+
+    clocks = ClockSampler(local).start()
+
+    # ---- headline: K steps (fwd + bwd), one CUDA graph, device-resident inputs ---------------------------------
+    chunk = min(K, 500)  # graph of `chunk` steps replayed K/chunk times (K rounded down to a multiple)
+    reps = max(1, K // chunk)
+    K_eff = chunk * reps
+    g_step, launches = capture(step, chunk)
+    ms_total = time_graph(g_step, reps)
+    ms_per_step = ms_total / K_eff
+    value = w.samples * world / (ms_per_step * 1e-3) / 1e9
+
+    # ---- per-pass timing for the roofline: forward-only and backward-only graphs -----------------------------
+    g_f, lf = capture(lambda i: fwd(sets[i % n_sets]), chunk)
+    ms_fwd = time_graph(g_f, reps) / K_eff
+    g_b, lb = capture(lambda i: bwd(sets[i % n_sets]), chunk)
+    ms_bwd = time_graph(g_b, reps) / K_eff
+    peak, peak_src = hbm_peak()
+
+    def roof(bytes_, ms, what):
+        ach = bytes_ / (ms * 1e-3) / 1e9
+        return {"bound": "hbm", "kernel": what, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
+                "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": bytes_, "us_per_launch": round(ms * 1e3, 3),
+                "peak_source": peak_src}
+
+    r_fwd = roof(w.algorithmic_bytes(elt, False), ms_fwd, "msda_fwd_vec_kernel (forward pass)")
+    r_bwd = roof(w.algorithmic_bytes(elt, True), ms_bwd, "msda_zero_kernel + msda_bwd_vec_kernel (backward pass)")
+    dominant = r_bwd if ms_bwd >= ms_fwd else r_fwd
+
+    # ---- eager (no graph) rate: what a Python caller gets launch-by-launch ------------------------------------
+    barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    n_eager = min(K_eff, 300)
+    e0.record()
+    for i in range(n_eager):
+        step(i)
+    e1.record()
+    barrier()
+    ms_eager = e0.elapsed_time(e1) / n_eager
+
+    # ---- end to end: pinned host inputs -> H2D -> fwd + bwd -> D2H of out + 3 grads, pipelined over 3 streams ----
+    e2e = None
+    if not args.no_e2e:
+        e2e = run_e2e(torch, msda, sets, w, dev, world, dist, min(K_eff, 200), elt)
+
+    clk = clocks.stop()
+
+    extra = {}
+    if args.extra and rank == 0:
+        extra = run_extra(torch, msda, _capi, dev, tdt, elt, peak)
+
+    cpu_base = None
+    if rank == 0 and not args.no_cpu_baseline:
+        rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=12.0, loc_mode=args.loc_mode)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": f"{desc}; {n} steps of fwd+autograd-bwd, {ms:.1f} ms/step (oracle/msda_torch_port.py)"}
+
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K_eff, "warmup": W,
+            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": args.dtype, "data": "synthetic",
+            "config": {
+                "workload": f"{w.name} per GPU: N={w.N}, levels={[list(l) for l in w.levels]}, Lq={w.Lq}, M={w.M}, "
+                            f"P={w.P}, D={w.D}, loc={args.loc_mode}; step = forward + backward",
+                "samples_per_step_per_gpu": w.samples,
+                "l2_policy": f"rotating {n_sets} distinct input sets ({n_sets * step_bytes / 1e6:.0f} MB > 2x L2)",
+                "launch": f"CUDA graph of {chunk} steps x {reps} replays",
+                "sharding": "batch-sharded, no data-path collective",
+            },
+            "roofline": dominant, "roofline_fwd": r_fwd, "roofline_bwd": r_bwd,
+            "fwd_only": {"value": w.samples * world / (ms_fwd * 1e-3) / 1e9, "unit": UNIT, "us": ms_fwd * 1e3},
+            "bwd_only": {"value": w.samples * world / (ms_bwd * 1e-3) / 1e9, "unit": UNIT, "us": ms_bwd * 1e3},
+            "eager": {"value": w.samples * world / (ms_eager * 1e-3) / 1e9, "unit": UNIT, "us_per_step": ms_eager * 1e3},
+            "cpu_baseline": cpu_base, "e2e": e2e,
+            "gpu_launches": int(launches * reps), "launches_per_step": launches / chunk,
+            "clocks": clk,
+        }
+        if extra:
+            line["extra"] = extra
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
+    """Same step through the public API with HOST buffers: every step uploads its inputs from pinned memory and
+    downloads out + the three gradients.  3-stage pipeline (upload / compute / download streams)."""
+    names = ("value", "loc", "attn", "grad_out")
+    n_host = min(len(sets), 4)
+    host = [{k: sets[i][k].cpu().pin_memory() for k in names} for i in range(n_host)]
+    depth = 3
+    slots = []
+    for _ in range(depth):
+        s0 = sets[0]
+        slots.append({
+            "in": {k: torch.empty_like(s0[k]) for k in names},
+            "out_h": None, "ev_up": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_down": torch.cuda.Event(),
+        })
+    shapes, start = sets[0]["shapes"], sets[0]["start"]
+    s_up, s_cp, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
+    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in names)
+    out_shapes = [(w.N, w.Lq, w.M * w.D), (w.N, w.S, w.M, w.D), (w.N, w.Lq, w.M, w.L, w.P, 2), (w.N, w.Lq, w.M, w.L, w.P)]
+    for sl in slots:
+        sl["out_h"] = [torch.empty(s, dtype=sets[0]["value"].dtype).pin_memory() for s in out_shapes]
+    d2h = sum(t.numel() * t.element_size() for t in slots[0]["out_h"])
+
+    def run(n):
+        for i in range(n):
+            sl = slots[i % depth]
+            h = host[i % n_host]
+            with torch.cuda.stream(s_up):
+                s_up.wait_event(sl["ev_done"])  # slot inputs free once the previous compute on it finished
+                for k in names:
+                    sl["in"][k].copy_(h[k], non_blocking=True)
+                sl["ev_up"].record(s_up)
+            with torch.cuda.stream(s_cp):
+                s_cp.wait_event(sl["ev_up"])
+                x = sl["in"]
+                out = msda.ms_deform_attn_forward(x["value"], shapes, start, x["loc"], x["attn"])
+                gv, gl, ga = msda.ms_deform_attn_backward(x["value"], shapes, start, x["loc"], x["attn"], x["grad_out"])
+                sl["ev_done"].record(s_cp)
+            with torch.cuda.stream(s_dn):
+                s_dn.wait_event(sl["ev_done"])
+                s_dn.wait_event(sl["ev_down"])
+                for dst, src in zip(sl["out_h"], (out, gv, gl, ga)):
+                    dst.copy_(src, non_blocking=True)
+                    src.record_stream(s_dn)
+                sl["ev_down"].record(s_dn)
+        for s in (s_up, s_cp, s_dn):
+            s.synchronize()
+
+    run(depth * 2)
+    torch.cuda.synchronize()
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    run(K)
+    torch.cuda.synchronize()
+    e1.record()
+    torch.cuda.synchronize()
+    ms = max(e0.elapsed_time(e1), (time.perf_counter() - t0) * 1e3) / K
+    if world > 1:
+        t = torch.tensor([ms], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item())
+    return {"value": w.samples * world / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
+            "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": K,
+            "path": "pinned host -> H2D -> ms_deform_attn_forward + ms_deform_attn_backward (C ABI) -> D2H of out, grad_value, grad_loc, grad_attn; 3-slot pipeline on 3 streams"}
+
+
+def run_extra(torch, msda, _capi, dev, tdt, elt, peak):
+    """Other COCO shapes (not the headline): fwd and bwd us/launch and roofline fraction, device-resident."""
+    from aloception_oss_b200.synthetic import WORKLOADS, device_inputs
+
+    res = {}
+    for name, mode in (("C4DEC", "unit"), ("C5DEC", "unit"), ("ENC", "raster"), ("C5ENC", "raster"), ("C4ENC", "raster")):
+        w = WORKLOADS[name]
+        step_bytes = w.algorithmic_bytes(elt, False) + w.algorithmic_bytes(elt, True)
+        n_sets = max(2, min(8, int(2 * L2_BYTES / step_bytes) + 2))
+        sets = [device_inputs(w, seed=77 + i, device=dev, dtype=tdt, loc_mode=mode) for i in range(n_sets)]
+        out = {}
+        for what, fn in (("fwd", lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])),
+                         ("bwd", lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"]))):
+            for i in range(3):
+                fn(sets[i % n_sets])
+            torch.cuda.synchronize()
+            n = 40
+            g = torch.cuda.CUDAGraph()
+            with torch.cuda.graph(g):
+                for i in range(n):
+                    fn(sets[i % n_sets])
+            g.replay()
+            torch.cuda.synchronize()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            del g
+            us = e0.elapsed_time(e1) / n * 1e3
+            b = w.algorithmic_bytes(elt, what == "bwd")
+            out[what] = {"us": round(us, 2), "gsamples_per_s": round(w.samples / us / 1e3, 3),
+                         "hbm_frac": round(b / (us * 1e-6) / 1e9 / peak, 4)}
+        res[f"{name}[{mode}]"] = out
+        del sets
+        torch.cuda.empty_cache()
+    return res
+
+
+if __name__ == "__main__":
+    main()

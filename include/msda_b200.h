@@ -1,0 +1,119 @@
+/*
+ * msda_b200.h -- C ABI of the B200-native multi-scale deformable attention operator.
+ *
+ * This is the drop-in boundary for the reference's native op library
+ * `MultiScaleDeformableAttention.so` (torch namespace `alonet_custom`).  Every entry point names
+ * the reference interface it replaces; paths are relative to the reference repository root.
+ *
+ * Conventions
+ *   - plain C, no torch / ATen types; all tensor arguments are raw pointers into memory owned by the
+ *     caller, contiguous row-major; the library never allocates or frees caller tensors;
+ *   - `stream` is a `cudaStream_t` passed as `void*` (NULL = legacy default stream); every device entry
+ *     point only ENQUEUES work on it and never synchronises the host (the reference launches on
+ *     at::cuda::getCurrentCUDAStream(): alonet/deformable_detr/ops/src/cuda/ms_deform_attn_cuda.cu:65,135);
+ *   - return value 0 = success; non-zero = error, text available from msda_last_error_string()
+ *     (the reference only printf()s launch failures: ms_deform_im2col_cuda.cuh:948-952,1321-1325);
+ *   - thread-safe and re-entrant; no global state besides read-mostly tuning knobs.
+ *
+ * Tensor layouts (identical to the reference op, ms_deform_attn_cuda.cu:40-48):
+ *   value             (N, S, M, D)        S = sum_l H_l * W_l
+ *   spatial_shapes    (L, 2)  int32, DEVICE memory, (H_l, W_l)      [ms_deform_attn_cuda.cu:67]
+ *   level_start_index (L,)    int32, DEVICE memory                  [ms_deform_attn_cuda.cu:68]
+ *   sampling_loc      (N, Lq, M, L, P, 2) (x, y) normalised to [0,1]
+ *   attn_weight       (N, Lq, M, L, P)
+ *   output            (N, Lq, M*D)
+ */
+#ifndef MSDA_B200_H_
+#define MSDA_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define MSDA_ABI_VERSION 1
+
+/* Element type of value / sampling_loc / attn_weight / output / gradients.
+ * The reference op dispatches float and double only (AT_DISPATCH_FLOATING_TYPES,
+ * ms_deform_attn_cuda.cu:64,134); bf16 / f16 storage with fp32 arithmetic is an extension. */
+enum msda_dtype { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F16 = 2, MSDA_F64 = 3 };
+
+/* Problem sizes, in the reference's naming (ms_deform_attn_cuda.cu:40-48). */
+typedef struct msda_dims {
+  int batch;        /* N  = value.size(0)            */
+  int spatial_size; /* S  = value.size(1)            */
+  int num_heads;    /* M  = value.size(2)            */
+  int channels;     /* D  = value.size(3)            */
+  int num_levels;   /* L  = spatial_shapes.size(0)   */
+  int num_query;    /* Lq = sampling_loc.size(1)     */
+  int num_point;    /* P  = sampling_loc.size(4)     */
+} msda_dims;
+
+/* ABI version of the loaded library (== MSDA_ABI_VERSION it was built with). */
+int msda_version(void);
+
+/* Text of the last error raised on the calling thread ("" if none). */
+const char* msda_last_error_string(void);
+
+/*
+ * Forward.  Replaces `ms_deform_attn_cuda_forward` (ms_deform_attn_cuda.cu:20-80) together with its
+ * launcher `ms_deformable_im2col_cuda` and kernel `ms_deformable_im2col_gpu_kernel`
+ * (ms_deform_im2col_cuda.cuh:923-954, 237-299), i.e. the body of torch op
+ * `alonet_custom::ms_deform_attn_forward` (src/vision.cpp:22).
+ * `output` need not be initialised (every element is written).  `im2col_step` of the reference is a
+ * batching knob of its launcher only and has no equivalent here.
+ */
+int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                 const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims,
+                 int dtype, void* stream);
+
+/*
+ * Bytes of scratch `msda_backward` needs for this problem (0 for MSDA_F32 / MSDA_F64; an fp32
+ * accumulation image of grad_value for the 16-bit types).
+ */
+size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
+
+/*
+ * Backward.  Replaces `ms_deform_attn_cuda_backward` (ms_deform_attn_cuda.cu:83-153), the dispatcher
+ * `ms_deformable_col2im_cuda` and its six kernels (ms_deform_im2col_cuda.cuh:956-1327, 301-920), i.e. the
+ * body of torch op `alonet_custom::ms_deform_attn_backward` (src/vision.cpp:23).
+ * None of the three gradient tensors needs initialising: grad_value is zero-filled by the library,
+ * grad_sampling_loc and grad_attn_weight are written in full.
+ * `workspace` : device scratch of at least msda_backward_workspace_bytes() bytes (may be NULL when 0).
+ * `flags`     : reserved, pass 0.
+ */
+int msda_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
+                  const int32_t* level_start_index, const void* sampling_loc, const void* attn_weight,
+                  void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
+                  size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream);
+
+/*
+ * Host-buffer forward for callers without a device allocator (the TensorRT-plugin-style consumer,
+ * alonet/torch2trt/plugins/ms_deform_im2col/sources/ms_deform_im2col_kernel.cu:261-327, hands the kernel
+ * raw pointers in the same way).  All seven pointers are HOST memory (pinned memory makes the copies
+ * asynchronous); the call stages them through stream-ordered device allocations, runs the same kernel as
+ * msda_forward and returns after `output` is complete on the host.
+ */
+int msda_forward_host(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                      const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims,
+                      int dtype, void* stream);
+
+/*
+ * Tuning knobs (benchmark / test use).  Unknown names return non-zero.  Names:
+ *   "force_generic"    0|1   route every call through the shape-generic kernels
+ *   "fwd_unroll"       0=auto, 1, 2 or 4 samples in flight per lane group in the vector forward kernel
+ *   "bwd_unroll"       0=auto, 1, 2 or 4 likewise for the vector backward kernel
+ *   "warps_per_block"  0=auto, 1..32
+ */
+int msda_set_tuning(const char* name, int value);
+int msda_get_tuning(const char* name, int* value);
+
+/* Number of kernels this library has launched since load (all threads); for launch accounting. */
+uint64_t msda_kernel_launch_count(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* MSDA_B200_H_ */

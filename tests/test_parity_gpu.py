@@ -1,0 +1,277 @@
+"""GPU parity: the sm_100a operator (through the C ABI, via the reference-shaped Python surface) against the
+CPU oracle and the committed golden vectors of the reference.
+
+Tolerances (BASELINE.json north_star): fp32 1e-4 rtol, bf16/f16 1e-2 rtol; fp64 ~1e-10.  Gradient tensors add an
+absolute term of rtol * rms(reference) -- see tests/_util.assert_close_grad for why a purely relative bound
+cannot hold for fp32 channel sums.
+"""
+import numpy as np
+import pytest
+import torch
+
+import aloception_oss_b200 as msda
+from aloception_oss_b200 import _capi
+from aloception_oss_b200.synthetic import WORKLOADS, Workload, device_inputs, torch_inputs
+from oracle import msda_oracle
+from tests._util import assert_close, assert_close_grad, check_grad_value, golden_names, load_golden, rms
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.fixture(autouse=True)
+def _ops(cuda_device):
+    msda.load_ops()
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block"):
+        _capi.set_tuning(k, 0)
+    yield
+
+
+def run_op(x, dev, dtype=None, need_grad=True):
+    """x: dict of CPU tensors -> (out, gv, gl, ga) as float64 numpy, computed on the GPU."""
+    f = lambda t: (t.to(dtype) if dtype is not None else t).to(dev)
+    value, loc, attn, go = f(x["value"]), f(x["loc"]), f(x["attn"]), f(x["grad_out"])
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    if need_grad:
+        value.requires_grad_(True)
+        loc.requires_grad_(True)
+        attn.requires_grad_(True)
+    out = msda.MSDeformAttnFunction.apply(value, shapes, start, loc, attn, 64)
+    res = [out.detach().double().cpu().numpy()]
+    if need_grad:
+        out.backward(go)
+        res += [t.grad.double().cpu().numpy() for t in (value, loc, attn)]
+    torch.cuda.synchronize()
+    return res
+
+
+def oracle64(x):
+    n = {k: (v.double().numpy() if v.is_floating_point() else v.numpy()) for k, v in x.items()}
+    out = msda_oracle.forward(n["value"], n["shapes"], n["loc"], n["attn"], n["start"])
+    gv, gl, ga = msda_oracle.backward(n["grad_out"], n["value"], n["shapes"], n["loc"], n["attn"], n["start"])
+    return out, gv, gl, ga
+
+
+# ---------------------------------------------------------------------------------------------------------
+# golden vectors of the reference
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", golden_names())
+def test_golden(name, cuda_device):
+    w, x, ref = load_golden(name)
+    xt = {k: torch.from_numpy(v) for k, v in x.items()}
+    out, gv, gl, ga = run_op(xt, cuda_device)
+    if x["value"].dtype == np.float64:  # the reference's fp64 check (ops/test.py:36-66) + gradcheck cases
+        assert_close(out, ref["out"], 1e-10, 1e-15, "out")
+        assert_close(gl, ref["grad_loc"], 1e-9, 1e-14, "grad_loc")
+        assert_close(ga, ref["grad_attn"], 1e-9, 1e-14, "grad_attn")
+        check_grad_value(gv, ref, 1e-9, 1e-14)
+    else:
+        assert_close(out, ref["out64"], 1e-4, 1e-4 * 1e-3 * rms(ref["out64"]), "out")
+        assert_close_grad(gl, ref["grad_loc64"], 1e-4, "grad_loc")
+        assert_close_grad(ga, ref["grad_attn64"], 1e-4, "grad_attn")
+        check_grad_value(gv, ref, 1e-4)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# oracle comparisons over shapes / dtypes / kernels
+# ---------------------------------------------------------------------------------------------------------
+SHAPES = [
+    Workload("d32", 2, ((12, 16), (6, 8), (3, 4), (2, 2)), 37, M=8, P=4, D=32),
+    Workload("d32_p3_l3", 1, ((9, 5), (4, 3), (2, 1)), 19, M=5, P=3, D=32),     # L*P = 9: ragged lane groups
+    Workload("d64", 2, ((7, 9), (3, 5)), 11, M=4, P=4, D=64),
+    Workload("d16", 2, ((7, 9), (3, 5)), 11, M=4, P=2, D=16),
+    Workload("d128", 1, ((7, 9), (3, 5)), 5, M=2, P=4, D=128),
+    Workload("d30", 1, ((6, 4), (3, 2)), 2, M=2, P=2, D=30),                     # generic kernel (ops/test.py:130)
+    Workload("d71", 1, ((6, 4), (3, 2)), 2, M=2, P=2, D=71),
+    Workload("d1", 2, ((1, 1), (2, 3)), 3, M=1, P=1, D=1),
+    Workload("l1", 1, ((16, 16),), 33, M=8, P=4, D=32),
+    Workload("p17", 1, ((8, 8), (4, 4)), 9, M=2, P=17, D=32),
+]
+
+
+@pytest.mark.parametrize("w", SHAPES, ids=lambda w: w.name)
+@pytest.mark.parametrize("mode", ["unit", "wide"])
+def test_fp32_vs_oracle(w, mode, cuda_device):
+    x = torch_inputs(w, seed=13, loc_mode=mode)
+    got = run_op(x, cuda_device)
+    want = oracle64(x)
+    assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
+    check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
+    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
+
+
+@pytest.mark.parametrize("w", SHAPES, ids=lambda w: w.name)
+def test_fp64_vs_oracle(w, cuda_device):
+    x = torch_inputs(w, seed=14, loc_mode="wide", dtype=torch.float64)
+    got = run_op(x, cuda_device)
+    want = oracle64(x)
+    for g, wnt, n in zip(got, want, ("out", "grad_value", "grad_loc", "grad_attn")):
+        assert_close(g, wnt, 1e-9, 1e-13, n)
+
+
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("w", SHAPES[:6], ids=lambda w: w.name)
+def test_16bit_vs_oracle(w, dtype, cuda_device):
+    """16-bit storage, fp32 arithmetic: compare with the oracle evaluated on the SAME rounded inputs."""
+    x = torch_inputs(w, seed=15, loc_mode="unit")
+    xr = {k: (v.to(dtype).float() if v.is_floating_point() else v) for k, v in x.items()}
+    got = run_op(xr, cuda_device, dtype=dtype)
+    want = oracle64(xr)
+    assert_close(got[0], want[0], 1e-2, 1e-2 * rms(want[0]), "out")
+    assert_close(got[1], want[1], 1e-2, 1e-2 * rms(want[1]), "grad_value")
+    assert_close(got[2], want[2], 1e-2, 1e-2 * rms(want[2]), "grad_loc")
+    assert_close(got[3], want[3], 1e-2, 1e-2 * rms(want[3]), "grad_attn")
+
+
+@pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 1), ("fwd_unroll", 2), ("bwd_unroll", 1),
+                                      ("bwd_unroll", 4), ("warps_per_block", 3)])
+def test_kernel_variants_agree(knob, val, cuda_device):
+    w = SHAPES[0]
+    x = torch_inputs(w, seed=16, loc_mode="wide")
+    want = oracle64(x)
+    _capi.set_tuning(knob, val)
+    got = run_op(x, cuda_device)
+    assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
+    check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
+    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
+
+
+# ---------------------------------------------------------------------------------------------------------
+# edge cases
+# ---------------------------------------------------------------------------------------------------------
+def test_exact_window_edges_and_pixel_centres(cuda_device):
+    """Locations exactly on the skip-window borders, pixel centres and integer coordinates."""
+    w = Workload("edge", 1, ((4, 4), (2, 2)), 4, M=1, P=4, D=32)
+    x = torch_inputs(w, seed=1)
+    vals = torch.tensor([-0.125, 0.0, 0.125, 0.375, 0.5, 0.875, 1.0, 1.125, 1.25, -0.25])
+    idx = torch.arange(x["loc"].numel()) % vals.numel()
+    x["loc"] = vals[idx].view_as(x["loc"]).contiguous()
+    got = run_op(x, cuda_device, need_grad=False)
+    want = oracle64(x)
+    assert_close(got[0], want[0], 1e-5, 1e-9, "out")
+
+
+def test_all_samples_outside_gives_zero(cuda_device):
+    w = Workload("outside", 1, ((5, 5),), 3, M=2, P=2, D=32)
+    x = torch_inputs(w, seed=2)
+    x["loc"] = torch.full_like(x["loc"], 7.5)
+    out, gv, gl, ga = run_op(x, cuda_device)
+    assert not out.any() and not gv.any() and not gl.any() and not ga.any()
+
+
+@pytest.mark.parametrize("field,val", [("N", 0), ("Lq", 0)])
+def test_empty_inputs(field, val, cuda_device):
+    base = dict(N=2, Lq=5)
+    base[field] = val
+    w = Workload("empty", base["N"], ((3, 3),), base["Lq"], M=2, P=2, D=32)
+    x = torch_inputs(w, seed=2)
+    out, gv, gl, ga = run_op(x, cuda_device)
+    assert out.shape == (w.N, w.Lq, w.M * w.D)
+    assert gv.shape == (w.N, w.S, w.M, w.D) and not gv.any()
+
+
+def test_unaligned_views_use_generic_path(cuda_device):
+    """A value view that starts 4 bytes into its storage cannot use 128-bit loads; result must not change."""
+    w = SHAPES[0]
+    x = torch_inputs(w, seed=17)
+    want = oracle64(x)
+    dev = cuda_device
+    buf = torch.empty(x["value"].numel() + 1, device=dev)
+    v = buf[1:].view_as(x["value"])
+    v.copy_(x["value"])
+    assert v.is_contiguous() and v.data_ptr() % 16 != 0
+    out = msda.ms_deform_attn_forward(v, x["shapes"].to(dev), x["start"].to(dev), x["loc"].to(dev), x["attn"].to(dev))
+    assert_close(out.double().cpu().numpy(), want[0], 1e-4, 1e-7 * rms(want[0]))
+
+
+def test_int64_level_tensors_accepted(cuda_device):
+    w = SHAPES[0]
+    x = torch_inputs(w, seed=18)
+    dev = cuda_device
+    a = msda.ms_deform_attn_forward(x["value"].to(dev), x["shapes"].to(dev), x["start"].to(dev), x["loc"].to(dev), x["attn"].to(dev))
+    b = msda.ms_deform_attn_forward(x["value"].to(dev), x["shapes"].long().to(dev), x["start"].long().to(dev), x["loc"].to(dev), x["attn"].to(dev))
+    assert torch.equal(a, b)
+
+
+def test_error_behaviour_matches_reference(cuda_device):
+    w = SHAPES[0]
+    x = {k: v.to(cuda_device) for k, v in torch_inputs(w, seed=19).items()}
+    with pytest.raises(RuntimeError, match="value tensor has to be contiguous"):
+        msda.ms_deform_attn_forward(x["value"].transpose(2, 3), x["shapes"], x["start"], x["loc"], x["attn"])
+    with pytest.raises(RuntimeError, match="sampling_loc must be a CUDA tensor"):
+        msda.ms_deform_attn_forward(x["value"], x["shapes"], x["start"], x["loc"].cpu(), x["attn"])
+    with pytest.raises(RuntimeError, match="Not implemented on the CPU"):
+        torch.ops.alonet_custom.ms_deform_attn_forward(x["value"].cpu(), x["shapes"].cpu(), x["start"].cpu(), x["loc"].cpu(), x["attn"].cpu(), 64)
+    with pytest.raises(RuntimeError, match="must divide im2col_step"):
+        v3 = torch.cat([x["value"], x["value"][:1]]); l3 = torch.cat([x["loc"], x["loc"][:1]]); a3 = torch.cat([x["attn"], x["attn"][:1]])
+        msda.ms_deform_attn_forward(v3, x["shapes"], x["start"], l3, a3, im2col_step=2)
+
+
+# ---------------------------------------------------------------------------------------------------------
+# full-size configurations: size-independent properties
+# ---------------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("name", ["C2", "C5DEC", "C5ENC"])
+def test_full_size_properties(name, cuda_device):
+    w = WORKLOADS[name]
+    x = device_inputs(w, seed=5, device=cuda_device, loc_mode="unit")
+    fwd = lambda v, a=None: msda.ms_deform_attn_forward(v, x["shapes"], x["start"], x["loc"], x["attn"] if a is None else a)
+    out = fwd(x["value"])
+    # (1) linearity in value
+    v2 = torch.rand_like(x["value"])
+    lhs = fwd(2.0 * x["value"] + 0.5 * v2)
+    rhs = 2.0 * out + 0.5 * fwd(v2)
+    assert torch.allclose(lhs, rhs, rtol=1e-4, atol=1e-6)
+    # (2) partition of unity: constant value, locations well inside every level -> out = sum of weights = 1
+    loc_in = x["loc"] * 0.8 + 0.1
+    ones = torch.ones_like(x["value"])
+    o1 = msda.ms_deform_attn_forward(ones, x["shapes"], x["start"], loc_in, x["attn"])
+    assert torch.allclose(o1, torch.ones_like(o1), rtol=1e-5, atol=1e-5)
+    # (3) adjointness: <out(value), g> == <value, grad_value(g)>  (forward is linear in value)
+    gv, gl, ga = msda.ms_deform_attn_backward(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"])
+    a = (out.double() * x["grad_out"].double()).sum()
+    b = (x["value"].double() * gv.double()).sum()
+    assert abs(a - b) <= 1e-4 * max(abs(a), abs(b)) + 1e-9, (a, b)
+    # (4) <attn, grad_attn> == <out, g> as well (forward is linear in the weights)
+    c = (x["attn"].double() * ga.double()).sum()
+    assert abs(a - c) <= 1e-4 * max(abs(a), abs(c)) + 1e-9, (a, c)
+    # (5) batch independence (the sharding property): the first image alone gives the same rows
+    o_first = msda.ms_deform_attn_forward(x["value"][:1].contiguous(), x["shapes"], x["start"], x["loc"][:1].contiguous(), x["attn"][:1].contiguous())
+    assert torch.equal(o_first, out[:1])
+
+
+def test_c2_against_oracle_full(cuda_device):
+    """BASELINE.json configs[1]/[2] at full size against the C oracle (runs in ~1 s on the host)."""
+    w = WORKLOADS["C2"]
+    x = torch_inputs(w, seed=23, loc_mode="wide")
+    got = run_op(x, cuda_device)
+    want = oracle64(x)
+    assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
+    check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
+    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
+
+
+def test_module_matches_its_tracing_path(cuda_device):
+    """MSDeformAttn through the CUDA op == the same module through the traceable pure-PyTorch graph."""
+    torch.manual_seed(0)
+    dev = cuda_device
+    mod = msda.MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():  # make offsets/weights input-dependent (they are zero-initialised)
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    levels = ((16, 20), (8, 10), (4, 5), (2, 3))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    N, Lq = 2, 50
+    q = torch.randn(N, Lq, 256, device=dev)
+    src = torch.randn(N, S, 256, device=dev)
+    ref2 = torch.rand(N, Lq, 4, 2, device=dev)
+    ref4 = torch.cat([ref2, torch.rand(N, Lq, 4, 2, device=dev) * 0.3], -1)
+    mask = torch.zeros(N, S, dtype=torch.bool, device=dev)
+    mask[:, -7:] = True
+    for refp in (ref2, ref4):
+        a = mod(q, refp, src, shapes, start, mask)
+        b = mod(q, refp, src, shapes, start, mask, is_tracing=None)
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (a - b).abs().max()
