@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_variant{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -75,6 +75,24 @@ Launch unit_launch(long long units, int default_warps) {
   return l;
 }
 
+// one warp per unit, grid.y = image (the "sg" kernels use 32-bit in-image indexing)
+Launch image_launch(const msda_dims& d, int default_warps) {
+  int wpb = g_warps_per_block.load(std::memory_order_relaxed);
+  if (wpb <= 0 || wpb > MSDA_MAX_THREADS / 32) wpb = default_warps;
+  const long long qm = (long long)d.num_query * d.num_heads;
+  Launch l;
+  l.block = dim3(32 * wpb);
+  l.grid = dim3((unsigned)((qm + wpb - 1) / wpb), (unsigned)d.batch);
+  return l;
+}
+
+// preconditions of the sample-geometry kernels: 32-bit in-image offsets with 4 flag bits, grid.y = batch
+bool sg_ok(const msda_dims& d) {
+  return g_variant.load(std::memory_order_relaxed) == 0 && d.batch <= 65535 &&
+         (long long)d.spatial_size * d.num_heads * d.channels <= (1LL << 27) &&
+         (long long)d.num_query * d.num_heads < (1LL << 31) - 64;
+}
+
 int pick_unroll(int knob, int fallback) {
   const int u = knob;
   return (u == 1 || u == 2 || u == 4) ? u : fallback;
@@ -86,8 +104,19 @@ int pick_unroll(int knob, int fallback) {
 template <typename T, int D>
 int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
                    void* out, const msda_dims& d, long long units, cudaStream_t st) {
-  const Launch l = unit_launch(units, 8);
-  const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 4);
+  const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
+  if (sg_ok(d)) {
+    const Launch l = image_launch(d, 2);
+    const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+#define MSDA_FWD_SG(UU)                                                                                       \
+  msda::msda_fwd_sg_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                             \
+      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
+      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads)
+    if (U == 1) MSDA_FWD_SG(1); else if (U == 2) MSDA_FWD_SG(2); else MSDA_FWD_SG(4);
+#undef MSDA_FWD_SG
+    return check_launch("msda_forward(vector/sg)");
+  }
+  const Launch l = unit_launch(units, 2);
 #define MSDA_FWD(UU)                                                                                          \
   msda::msda_fwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
       (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
@@ -147,8 +176,19 @@ template <typename T, int D>
 int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
                    const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, long long units,
                    cudaStream_t st) {
-  const Launch l = unit_launch(units, 8);
-  const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 2);
+  const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 1);
+  if (sg_ok(d)) {
+    const Launch l = image_launch(d, 2);
+    const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+#define MSDA_BWD_SG(UU)                                                                                       \
+  msda::msda_bwd_sg_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                             \
+      (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, gv, (T*)gloc, (T*)gattn,    \
+      d.spatial_size, d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads)
+    if (U == 1) MSDA_BWD_SG(1); else if (U == 2) MSDA_BWD_SG(2); else MSDA_BWD_SG(4);
+#undef MSDA_BWD_SG
+    return check_launch("msda_backward(vector/sg)");
+  }
+  const Launch l = unit_launch(units, 2);
 #define MSDA_BWD(UU)                                                                                          \
   msda::msda_bwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
       (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, gv, (T*)gloc, (T*)gattn,    \
@@ -226,6 +266,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "fwd_unroll")) return &g_fwd_unroll;
   if (!strcmp(name, "bwd_unroll")) return &g_bwd_unroll;
   if (!strcmp(name, "warps_per_block")) return &g_warps_per_block;
+  if (!strcmp(name, "variant")) return &g_variant;
   return nullptr;
 }
 

@@ -162,6 +162,12 @@ __device__ __forceinline__ float load_s(const __half* p) {
   return __half2float(*reinterpret_cast<const __half*>(&h));
 }
 
+__device__ __forceinline__ void store_xy(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
+__device__ __forceinline__ void store_xy(__nv_bfloat16* p, float x, float y) {
+  *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
+}
+__device__ __forceinline__ void store_xy(__half* p, float x, float y) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(x, y); }
+
 // vectorised fp32 reduction into global memory (sm_90+): one 16-byte L2 atomic instead of four
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -394,6 +400,233 @@ msda_bwd_vec_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         gl[0] = from_acc<T>((float)ge[j].W * a[j] * s_x);
         gl[1] = from_acc<T>((float)Hs[j] * a[j] * s_y);
       }
+    }
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
+// VECTOR kernels, "sample-geometry" variant (default)
+// ------------------------------------------------------------------------------------------------
+// In the kernels above all LPR lanes of a group redo the coordinate -> tap-address arithmetic of their
+// sample (~55 instructions), so a (b,q,m) unit with 16 samples costs ~600 warp instructions and the SMs are
+// issue-bound for a good part of the run.  Here lane i of the warp does that arithmetic ONCE for sample i
+// (one coalesced read of the unit's 128-byte location block, 64-byte weight block), and the lane groups
+// fetch {tap offset, row stride | validity bits, 4 weights} of the sample they gather with warp shuffles.
+// Offsets are 32-bit (host checks S*M*D <= 2^27).  Grid: x = units of one image, y = image.
+struct SampleGeo {
+  int off00;   // element offset of tap (y0, x0) from the image base (head/channel offset NOT included)
+  int rsf;     // (W * M * D) << 4 | ok11 << 3 | ok10 << 2 | ok01 << 1 | ok00
+};
+
+template <typename T>
+__device__ __forceinline__ void sample_geometry(const T* __restrict__ u_loc, const T* __restrict__ u_att,
+                                                const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                                                int s, bool have, float inv_p, int MD, SampleGeo& sg, Geo<float>& ge,
+                                                float& a, int& H, int& W) {
+  const int si = have ? s : 0;
+  const int l = have ? level_of(si, inv_p) : 0;
+  float lx, ly;
+  load_xy(u_loc + 2 * si, lx, ly);
+  a = load_s(u_att + si);
+  H = __ldg(shapes + 2 * l);
+  W = __ldg(shapes + 2 * l + 1);
+  const int st = __ldg(start + l);
+  ge = make_geo<float>(lx, ly, H, W, have);
+  sg.off00 = (st + ge.row00) * MD;
+  sg.rsf = ((W * MD) << 4) | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
+}
+
+template <typename T, int D, int U>
+__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
+                   const int32_t* __restrict__ start, const T* __restrict__ loc,
+                   const T* __restrict__ attn, T* __restrict__ out,
+                   int S, int M, int L, int P, float inv_p, int QM) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  constexpr int G = 32 / LPR;
+  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
+
+  const int lane = threadIdx.x & 31;
+  const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // unit inside image blockIdx.y
+  if (uq >= QM) return;                                                // warp-uniform
+  const int g = lane / LPR, cl = lane % LPR;
+  const int m = uq % M;
+  const int LP = L * P;
+  const int MD = M * D;
+  const long long u = (long long)blockIdx.y * QM + uq;
+  const T* __restrict__ u_loc = loc + u * LP * 2;
+  const T* __restrict__ u_att = attn + u * LP;
+  const T* __restrict__ vb = value + (long long)blockIdx.y * S * MD + m * D + cl * VEC;
+  const T* zp = reinterpret_cast<const T*>(g_zero_line);
+
+  float acc[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+
+  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane
+    SampleGeo sg;
+    Geo<float> ge;
+    float a;
+    int H, W;
+    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, base + lane < LP, inv_p, MD, sg, ge, a, H, W);
+    const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
+    const int cnt = min(32, LP - base);
+    for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
+      const T* tp[U][4];
+      float w[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int src = k0 + j * G + g;
+        const int off = __shfl_sync(0xffffffffu, sg.off00, src);
+        int rsf = __shfl_sync(0xffffffffu, sg.rsf, src);
+        w[j][0] = __shfl_sync(0xffffffffu, w00, src);
+        w[j][1] = __shfl_sync(0xffffffffu, w01, src);
+        w[j][2] = __shfl_sync(0xffffffffu, w10, src);
+        w[j][3] = __shfl_sync(0xffffffffu, w11, src);
+        if (src >= cnt) rsf = 0;  // shfl wraps modulo 32: a lane group past the end must not gather
+        const T* t0 = vb + off;
+        const int rs = rsf >> 4;
+        tp[j][0] = (rsf & 1) ? t0 : zp;
+        tp[j][1] = (rsf & 2) ? t0 + MD : zp;
+        tp[j][2] = (rsf & 4) ? t0 + rs : zp;
+        tp[j][3] = (rsf & 8) ? t0 + rs + MD : zp;
+      }
+      uint4 v[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float f[VEC];
+          Vec16<T>::unpack(v[j][t], f);
+#pragma unroll
+          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w[j][t], f[i], acc[i]);
+        }
+    }
+  }
+#pragma unroll
+  for (int off = LPR; off < 32; off <<= 1)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
+  if (g == 0) *reinterpret_cast<uint4*>(out + u * D + cl * VEC) = Vec16<T>::pack(acc);
+}
+
+template <typename T, int D, int U>
+__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
+                   const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                   const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
+                   T* __restrict__ gloc, T* __restrict__ gattn,
+                   int S, int M, int L, int P, float inv_p, int QM) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  constexpr int G = 32 / LPR;
+  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
+
+  const int lane = threadIdx.x & 31;
+  const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (uq >= QM) return;
+  const int g = lane / LPR, cl = lane % LPR;
+  const int m = uq % M;
+  const int LP = L * P;
+  const int MD = M * D;
+  const long long u = (long long)blockIdx.y * QM + uq;
+  const T* __restrict__ u_loc = loc + u * LP * 2;
+  const T* __restrict__ u_att = attn + u * LP;
+  const long long voff = (long long)blockIdx.y * S * MD + m * D + cl * VEC;
+  const T* __restrict__ vb = value + voff;
+  float* __restrict__ gb = gv + voff;
+  const T* zp = reinterpret_cast<const T*>(g_zero_line);
+
+  float go[VEC];
+  Vec16<T>::unpack(ldg128(grad_out + u * D + cl * VEC), go);
+
+  for (int base = 0; base < LP; base += 32) {
+    SampleGeo sg;
+    Geo<float> ge;
+    float a;
+    int H, W;
+    const bool have = base + lane < LP;
+    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, MD, sg, ge, a, H, W);
+    const int cnt = min(32, LP - base);
+    float r_a = 0.f, r_x = 0.f, r_y = 0.f;  // channel sums of MY sample, collected from the group that gathered it
+    for (int k0 = 0; k0 < cnt; k0 += G * U) {
+      const T* tp[U][4];
+      int off[U], rsf[U];
+      float fly[U], flx[U], fa[U];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int src = k0 + j * G + g;
+        off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
+        rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
+        fly[j] = __shfl_sync(0xffffffffu, ge.ly, src);
+        flx[j] = __shfl_sync(0xffffffffu, ge.lx, src);
+        fa[j] = __shfl_sync(0xffffffffu, a, src);
+        if (src >= cnt) rsf[j] = 0;
+        const T* t0 = vb + off[j];
+        const int rs = rsf[j] >> 4;
+        tp[j][0] = (rsf[j] & 1) ? t0 : zp;
+        tp[j][1] = (rsf[j] & 2) ? t0 + MD : zp;
+        tp[j][2] = (rsf[j] & 4) ? t0 + rs : zp;
+        tp[j][3] = (rsf[j] & 8) ? t0 + rs + MD : zp;
+      }
+      uint4 v[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        float f00[VEC], f01[VEC], f10[VEC], f11[VEC];
+        Vec16<T>::unpack(v[j][0], f00);
+        Vec16<T>::unpack(v[j][1], f01);
+        Vec16<T>::unpack(v[j][2], f10);
+        Vec16<T>::unpack(v[j][3], f11);
+        const float ly_ = fly[j], lx_ = flx[j], hy = 1.f - ly_, hx = 1.f - lx_;
+        float s_a = 0.f, s_x = 0.f, s_y = 0.f;
+#pragma unroll
+        for (int i = 0; i < VEC; ++i) {
+          const float top = hx * f00[i] + lx_ * f01[i];  // interpolated along x on row y0
+          const float bot = hx * f10[i] + lx_ * f11[i];  // ... on row y0+1
+          s_a = fmaf(go[i], hy * top + ly_ * bot, s_a);
+          s_y = fmaf(go[i], bot - top, s_y);
+          s_x = fmaf(go[i], hy * (f01[i] - f00[i]) + ly_ * (f11[i] - f10[i]), s_x);
+        }
+        {  // scatter into grad_value: bilinear weight * attention * grad_out
+          float* g0 = gb + off[j];
+          const int rs = rsf[j] >> 4;
+          const float w00 = hy * hx * fa[j], w01 = hy * lx_ * fa[j], w10 = ly_ * hx * fa[j], w11 = ly_ * lx_ * fa[j];
+#pragma unroll
+          for (int i = 0; i < VEC; i += 4) {
+            if (rsf[j] & 1) red_add_v4(g0 + i, w00 * go[i], w00 * go[i + 1], w00 * go[i + 2], w00 * go[i + 3]);
+            if (rsf[j] & 2) red_add_v4(g0 + MD + i, w01 * go[i], w01 * go[i + 1], w01 * go[i + 2], w01 * go[i + 3]);
+            if (rsf[j] & 4) red_add_v4(g0 + rs + i, w10 * go[i], w10 * go[i + 1], w10 * go[i + 2], w10 * go[i + 3]);
+            if (rsf[j] & 8) red_add_v4(g0 + rs + MD + i, w11 * go[i], w11 * go[i + 1], w11 * go[i + 2], w11 * go[i + 3]);
+          }
+        }
+#pragma unroll
+        for (int o = 1; o < LPR; o <<= 1) {  // channel sums over the LPR lanes of this group
+          s_a += __shfl_xor_sync(0xffffffffu, s_a, o);
+          s_x += __shfl_xor_sync(0xffffffffu, s_x, o);
+          s_y += __shfl_xor_sync(0xffffffffu, s_y, o);
+        }
+        // hand the sums back to the lane that owns the sample: lane (k0 + j*G + g') reads from group g'
+        const int rel = lane - k0 - j * G;
+        const int from = (rel & (G - 1)) * LPR;
+        const float t_a = __shfl_sync(0xffffffffu, s_a, from);
+        const float t_x = __shfl_sync(0xffffffffu, s_x, from);
+        const float t_y = __shfl_sync(0xffffffffu, s_y, from);
+        if (rel >= 0 && rel < G) { r_a = t_a; r_x = t_x; r_y = t_y; }
+      }
+    }
+    if (have) {  // coalesced: 32 consecutive samples of the unit
+      const long long sidx = u * LP + base + lane;
+      gattn[sidx] = from_acc<T>(r_a);
+      store_xy(gloc + 2 * sidx, (float)W * a * r_x, (float)H * a * r_y);
     }
   }
 }

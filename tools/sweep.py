@@ -48,6 +48,8 @@ def main():
     ap.add_argument("--dtype", default="f32")
     ap.add_argument("--unrolls", default="1,2,4")
     ap.add_argument("--wpbs", default="2,4,8")
+    ap.add_argument("--variants", default="0,1")
+    ap.add_argument("--max-sets", type=int, default=24)
     args = ap.parse_args()
     msda.load_ops()
     dev = torch.device("cuda:0")
@@ -64,17 +66,18 @@ def main():
             w = WORKLOADS[name]
             mode = "raster" if w.Lq == w.S else "unit"
             sb = w.algorithmic_bytes(elt, False) + w.algorithmic_bytes(elt, True)
-            n_sets = max(2, min(10, int(2 * L2 / sb) + 2))
+            n_sets = max(2, min(args.max_sets, int(6 * L2 / sb) + 2))  # touched rows are sparse: over-provision
             sets = [device_inputs(w, seed=5 + i, device=dev, dtype=tdt, loc_mode=mode) for i in range(n_sets)]
             fwd = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
             bwd = lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
-            for u, wpb in itertools.product([int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+            for var, u, wpb in itertools.product([int(x) for x in args.variants.split(",")], [int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+                _capi.set_tuning("variant", var)
                 _capi.set_tuning("warps_per_block", wpb)
                 _capi.set_tuning("fwd_unroll", u)
                 _capi.set_tuning("bwd_unroll", u)
                 tf = time_graph(fwd, sets)
                 tb = time_graph(bwd, sets)
-                rec = dict(workload=name, dtype=args.dtype, loc=mode, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
+                rec = dict(workload=name, dtype=args.dtype, loc=mode, sets=n_sets, variant=var, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
                            fwd_frac=round(w.algorithmic_bytes(elt, False) / tf / 1e3 / peak, 4),
                            bwd_frac=round(w.algorithmic_bytes(elt, True) / tb / 1e3 / peak, 4),
                            fwd_gsps=round(w.samples / tf / 1e3, 3), bwd_gsps=round(w.samples / tb / 1e3, 3))
