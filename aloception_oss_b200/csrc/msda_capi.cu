@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_variant{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -86,9 +86,9 @@ Launch image_launch(const msda_dims& d, int default_warps) {
   return l;
 }
 
-// preconditions of the sample-geometry kernels: 32-bit in-image offsets with 4 flag bits, grid.y = batch
-bool sg_ok(const msda_dims& d) {
-  return g_variant.load(std::memory_order_relaxed) == 0 && d.batch <= 65535 &&
+// preconditions of the vector kernels: 32-bit in-image offsets with 4 flag bits, grid.y = batch
+bool vec_shape_ok(const msda_dims& d) {
+  return !g_force_generic.load(std::memory_order_relaxed) && d.batch <= 65535 && d.num_point < (1 << 15) &&
          (long long)d.spatial_size * d.num_heads * d.channels <= (1LL << 27) &&
          (long long)d.num_query * d.num_heads < (1LL << 31) - 64;
 }
@@ -101,26 +101,16 @@ int pick_unroll(int knob, int fallback) {
 // ---------------------------------------------------------------------------------------------
 // forward dispatch
 // ---------------------------------------------------------------------------------------------
-template <typename T, int D>
+template <typename T, int D, int MC>
 int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
-                   void* out, const msda_dims& d, long long units, cudaStream_t st) {
+                   void* out, const msda_dims& d, cudaStream_t st) {
   const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
-  if (sg_ok(d)) {
-    const Launch l = image_launch(d, 2);
-    const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
-#define MSDA_FWD_SG(UU)                                                                                       \
-  msda::msda_fwd_sg_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                             \
+  const Launch l = image_launch(d, 2);
+  const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+#define MSDA_FWD(UU)                                                                                          \
+  msda::msda_fwd_sg_kernel<T, D, MC, UU><<<l.grid, l.block, 0, st>>>(                                         \
       (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
       d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads)
-    if (U == 1) MSDA_FWD_SG(1); else if (U == 2) MSDA_FWD_SG(2); else MSDA_FWD_SG(4);
-#undef MSDA_FWD_SG
-    return check_launch("msda_forward(vector/sg)");
-  }
-  const Launch l = unit_launch(units, 2);
-#define MSDA_FWD(UU)                                                                                          \
-  msda::msda_fwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
-      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
-      d.num_levels, d.num_query, d.num_point, 1.0f / (float)(d.num_point > 0 ? d.num_point : 1), units)
   if (U == 1) MSDA_FWD(1); else if (U == 2) MSDA_FWD(2); else MSDA_FWD(4);
 #undef MSDA_FWD
   return check_launch("msda_forward(vector)");
@@ -139,17 +129,21 @@ int launch_fwd_generic(const void* value, const int32_t* shapes, const int32_t* 
 template <typename T>
 int forward_typed(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
                   void* out, const msda_dims& d, long long units, cudaStream_t st) {
-  const bool vec_ok = !g_force_generic.load(std::memory_order_relaxed) && d.num_levels <= 32 &&
-                      d.num_point < (1 << 15) && aligned(value, 16) && aligned(out, 16) &&
-                      aligned(loc, 2 * sizeof(T)) && aligned(attn, sizeof(T));
+  const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(out, 16) && aligned(loc, 2 * sizeof(T)) &&
+                      aligned(attn, sizeof(T));
   if (vec_ok) {
+#define MSDA_CASE(DD)                                                                                         \
+  case DD:                                                                                                    \
+    return d.num_heads == 8 ? launch_fwd_vec<T, DD, 8>(value, shapes, start, loc, attn, out, d, st)           \
+                            : launch_fwd_vec<T, DD, 0>(value, shapes, start, loc, attn, out, d, st);
     switch (d.channels) {
-      case 16: return launch_fwd_vec<T, 16>(value, shapes, start, loc, attn, out, d, units, st);
-      case 32: return launch_fwd_vec<T, 32>(value, shapes, start, loc, attn, out, d, units, st);
-      case 64: return launch_fwd_vec<T, 64>(value, shapes, start, loc, attn, out, d, units, st);
-      case 128: return launch_fwd_vec<T, 128>(value, shapes, start, loc, attn, out, d, units, st);
+      MSDA_CASE(16)
+      MSDA_CASE(32)
+      MSDA_CASE(64)
+      MSDA_CASE(128)
       default: break;
     }
+#undef MSDA_CASE
   }
   return launch_fwd_generic<T>(value, shapes, start, loc, attn, out, d, units, st);
 }
@@ -165,38 +159,47 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   }
   const long long n16 = (long long)(bytes / 16);
   const int ntail = (int)(bytes % 16);
-  long long blocks = (n16 + 256 * 4 - 1) / (256 * 4);  // ~4 stores per thread
+  // every CTA must be resident at once: the dependent backward kernel is released when all of them have started
+  long long blocks = (n16 + 256 * 8 - 1) / (256 * 8);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 16) blocks = 148 * 16;
+  if (blocks > 148 * 4) blocks = 148 * 4;
   msda::msda_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, ntail);
   return check_launch("msda_backward(zero grad_value)");
 }
 
-template <typename T, int D>
+template <typename T, int D, int MC>
 int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
-                   const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, long long units,
-                   cudaStream_t st) {
+                   const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st) {
   const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 1);
-  if (sg_ok(d)) {
-    const Launch l = image_launch(d, 2);
-    const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
-#define MSDA_BWD_SG(UU)                                                                                       \
-  msda::msda_bwd_sg_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                             \
-      (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, gv, (T*)gloc, (T*)gattn,    \
-      d.spatial_size, d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads)
-    if (U == 1) MSDA_BWD_SG(1); else if (U == 2) MSDA_BWD_SG(2); else MSDA_BWD_SG(4);
-#undef MSDA_BWD_SG
-    return check_launch("msda_backward(vector/sg)");
-  }
-  const Launch l = unit_launch(units, 2);
+  const Launch l = image_launch(d, 2);
+  const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+  // Programmatic dependent launch: pass 1 of the kernel overlaps the zero-fill that precedes it in the stream;
+  // `griddepcontrol.wait` inside the kernel orders pass 2 (the scatter) after the fill.
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = l.grid;
+  cfg.blockDim = l.block;
+  cfg.dynamicSmemBytes = 0;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl.load(std::memory_order_relaxed) ? 0 : 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const T* go_ = (const T*)go; const T* value_ = (const T*)value; const T* loc_ = (const T*)loc; const T* attn_ = (const T*)attn;
+  T* gloc_ = (T*)gloc; T* gattn_ = (T*)gattn;
+  const int S = d.spatial_size, M = d.num_heads, L = d.num_levels, P = d.num_point, QM = d.num_query * d.num_heads;
+  cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
-  msda::msda_bwd_vec_kernel<T, D, UU><<<l.grid, l.block, 0, st>>>(                                            \
-      (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, gv, (T*)gloc, (T*)gattn,    \
-      d.spatial_size, d.num_heads, d.num_levels, d.num_query, d.num_point,                                     \
-      1.0f / (float)(d.num_point > 0 ? d.num_point : 1), units)
+  e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU>, go_, value_, shapes, start, loc_, attn_, gv, \
+                         gloc_, gattn_, S, M, L, P, inv_p, QM)
   if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4);
 #undef MSDA_BWD
-  return check_launch("msda_backward(vector)");
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("msda_backward(vector): CUDA launch failed: %s", cudaGetErrorString(e));
+  }
+  return 0;
 }
 
 template <typename T>
@@ -211,18 +214,24 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
   if (units > 0 && d.channels > 0 && d.num_levels * d.num_point > 0) {
     bool done = false;
     if constexpr (!std::is_same<T, double>::value) {
-      const bool vec_ok = !g_force_generic.load(std::memory_order_relaxed) && d.num_levels <= 32 &&
-                          d.num_point < (1 << 15) && aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) && aligned(loc, 2 * sizeof(T)) &&
-                          aligned(gloc, sizeof(T)) && aligned(attn, sizeof(T));
+      const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) &&
+                          aligned(loc, 2 * sizeof(T)) && aligned(gloc, 2 * sizeof(T)) && aligned(attn, sizeof(T));
       if (vec_ok) {
         int rc = -1;
+#define MSDA_CASE(DD)                                                                                         \
+  case DD:                                                                                                    \
+    rc = d.num_heads == 8                                                                                     \
+             ? launch_bwd_vec<T, DD, 8>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, st)  \
+             : launch_bwd_vec<T, DD, 0>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, st); \
+    break;
         switch (d.channels) {
-          case 16: rc = launch_bwd_vec<T, 16>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
-          case 32: rc = launch_bwd_vec<T, 32>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
-          case 64: rc = launch_bwd_vec<T, 64>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
-          case 128: rc = launch_bwd_vec<T, 128>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, units, st); break;
+          MSDA_CASE(16)
+          MSDA_CASE(32)
+          MSDA_CASE(64)
+          MSDA_CASE(128)
           default: break;
         }
+#undef MSDA_CASE
         if (rc > 0) return rc;
         done = rc == 0;
       }
@@ -246,10 +255,6 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
   return 0;
 }
 
-struct DeviceGuard {
-  // kernels launch on the device that owns `stream`'s context = the caller's current device; nothing to do.
-};
-
 }  // namespace
 
 extern "C" {
@@ -266,7 +271,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "fwd_unroll")) return &g_fwd_unroll;
   if (!strcmp(name, "bwd_unroll")) return &g_bwd_unroll;
   if (!strcmp(name, "warps_per_block")) return &g_warps_per_block;
-  if (!strcmp(name, "variant")) return &g_variant;
+  if (!strcmp(name, "no_pdl")) return &g_no_pdl;
   return nullptr;
 }
 

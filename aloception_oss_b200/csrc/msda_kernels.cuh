@@ -174,248 +174,32 @@ __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float 
 }
 
 // ------------------------------------------------------------------------------------------------
-// VECTOR kernels -- shared pieces
+// VECTOR kernels
 // ------------------------------------------------------------------------------------------------
-// Invalid taps (outside the level, or sample outside the window) read this line instead of being
-// predicated off: unconditional loads let ptxas issue all 4*U gathers of a lane back to back
-// (checked with tools/sass_summary.py); a predicated load sequence was serialised into load->FMA pairs.
+// T in {float, bf16, half}; a row of D channels is covered by LPR = D*sizeof(T)/16 lanes (one 128-bit load
+// each), so the warp holds G = 32/LPR lane groups that gather G different samples per load instruction.
+//
+// "Sample geometry": lane i of the warp turns sampling location i of the unit into {tap offset, row stride |
+// validity bits, weights} ONCE (one coalesced read of the unit's location / weight block); the lane groups
+// then fetch the record of the sample they gather with warp shuffles.  (Letting every lane of a group redo
+// that arithmetic cost ~600 warp instructions per unit and made the kernels issue-bound: profiles/.)
+//
+// Invalid taps (outside the level, or the sample outside the window) read g_zero_line instead of being
+// predicated off: unconditional loads keep the 4*U gathers of a lane back to back in the SASS
+// (tools/sass_summary.py).  When every tap of the warp's current samples is valid -- the common case -- a
+// warp-uniform fast path skips the pointer selects.
+//
+// MC > 0 fixes the head count at compile time (M*D*sizeof(T) becomes an immediate load offset); MC == 0 reads
+// it from the argument.  Offsets are 32-bit: the host checks S*M*D <= 2^27.  Grid: x = units of one image,
+// y = image.
 __device__ __align__(16) const unsigned int g_zero_line[4] = {0u, 0u, 0u, 0u};
-
-// Per-warp level table: lane l holds (H_l, W_l, start_l); read back with __shfl_sync.  Needs L <= 32.
-struct LevelTable {
-  int H, W, st;
-  __device__ __forceinline__ void load(const int32_t* __restrict__ shapes, const int32_t* __restrict__ start, int L, int lane) {
-    H = 1; W = 1; st = 0;
-    if (lane < L) {
-      H = __ldg(shapes + 2 * lane);
-      W = __ldg(shapes + 2 * lane + 1);
-      st = __ldg(start + lane);
-    }
-  }
-};
 
 // level of sample s (= s / P) without an integer division: exact for s, P < 2^20
 __device__ __forceinline__ int level_of(int s, float inv_p) { return __float2int_rz(((float)s + 0.5f) * inv_p); }
 
-// ------------------------------------------------------------------------------------------------
-// VECTOR FORWARD
-// ------------------------------------------------------------------------------------------------
-// T in {float, bf16, half}; D*sizeof(T)/16 = LPR in {1,2,4,8,16,32}; U samples in flight per lane group.
-// Dependent-latency chain per warp: {loc, attn, level table} -> 4*U tap rows -> shuffles -> store.
-template <typename T, int D, int U>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
-msda_fwd_vec_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
-                    const int32_t* __restrict__ start, const T* __restrict__ loc,
-                    const T* __restrict__ attn, T* __restrict__ out,
-                    int S, int M, int L, int Lq, int P, float inv_p, long long units) {
-  constexpr int VEC = Vec16<T>::N;
-  constexpr int LPR = D / VEC;
-  constexpr int G = 32 / LPR;
-  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
-
-  const int lane = threadIdx.x & 31;
-  const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= units) return;  // warp-uniform
-  const int g = lane / LPR, cl = lane % LPR;
-  const int m = (int)(u % M);
-  const long long b = (u / M) / Lq;
-  const int LP = L * P;
-  const int MD = M * D;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
-  const T* __restrict__ u_att = attn + u * LP;
-  const T* __restrict__ vb = value + b * (long long)S * MD + m * D + cl * VEC;
-  const T* zp = reinterpret_cast<const T*>(g_zero_line);
-
-  LevelTable lt;
-  lt.load(shapes, start, L, lane);
-
-  float acc[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
-
-  for (int s0 = g; s0 < LP + g; s0 += G * U) {  // same trip count for every group (warp-uniform loop)
-    float lx[U], ly[U], a[U];
-    int sc[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {  // phase 1: the small loads, all independent
-      const int s = s0 + j * G;
-      sc[j] = s < LP ? s : -1;
-      const int si = s < LP ? s : 0;
-      load_xy(u_loc + 2 * si, lx[j], ly[j]);
-      a[j] = load_s(u_att + si);
-    }
-    const T* tp[U][4];
-    float w[U][4];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {  // phase 2: geometry -> 4 tap addresses + weights
-      const bool valid = sc[j] >= 0;
-      const int l = valid ? level_of(sc[j], inv_p) : 0;
-      const int H = __shfl_sync(0xffffffffu, lt.H, l), W = __shfl_sync(0xffffffffu, lt.W, l);
-      const int st = __shfl_sync(0xffffffffu, lt.st, l);
-      const Geo<float> ge = make_geo<float>(lx[j], ly[j], H, W, valid);
-      w[j][0] = ge.hy * ge.hx * a[j]; w[j][1] = ge.hy * ge.lx * a[j];
-      w[j][2] = ge.ly * ge.hx * a[j]; w[j][3] = ge.ly * ge.lx * a[j];
-      const T* t0 = vb + ((long long)st + ge.row00) * MD;
-      const int rs = W * MD;
-      tp[j][0] = ge.ok00 ? t0 : zp;
-      tp[j][1] = ge.ok01 ? t0 + MD : zp;
-      tp[j][2] = ge.ok10 ? t0 + rs : zp;
-      tp[j][3] = ge.ok11 ? t0 + rs + MD : zp;
-    }
-    uint4 v[U][4];
-#pragma unroll
-    for (int j = 0; j < U; ++j)  // phase 3: 4*U independent 128-bit gathers
-#pragma unroll
-      for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
-#pragma unroll
-    for (int j = 0; j < U; ++j)  // phase 4: weighted accumulation
-#pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float f[VEC];
-        Vec16<T>::unpack(v[j][t], f);
-#pragma unroll
-        for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w[j][t], f[i], acc[i]);
-      }
-  }
-#pragma unroll
-  for (int off = LPR; off < 32; off <<= 1)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-  if (g == 0) *reinterpret_cast<uint4*>(out + u * D + cl * VEC) = Vec16<T>::pack(acc);
-}
-
-// ------------------------------------------------------------------------------------------------
-// VECTOR BACKWARD
-// ------------------------------------------------------------------------------------------------
-// grad_value accumulates in fp32 (`gv`): the caller's tensor for T=float, a workspace for 16-bit T.
-// Scatter = 16-byte `red.global.add.v4.f32` per tap per lane (no return value, resolved in L2).
-template <typename T, int D, int U>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
-msda_bwd_vec_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
-                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
-                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
-                    T* __restrict__ gloc, T* __restrict__ gattn,
-                    int S, int M, int L, int Lq, int P, float inv_p, long long units) {
-  constexpr int VEC = Vec16<T>::N;
-  constexpr int LPR = D / VEC;
-  constexpr int G = 32 / LPR;
-  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
-
-  const int lane = threadIdx.x & 31;
-  const long long u = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (u >= units) return;
-  const int g = lane / LPR, cl = lane % LPR;
-  const int m = (int)(u % M);
-  const long long b = (u / M) / Lq;
-  const int LP = L * P;
-  const int MD = M * D;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
-  const T* __restrict__ u_att = attn + u * LP;
-  const long long voff = b * (long long)S * MD + m * D + cl * VEC;
-  const T* __restrict__ vb = value + voff;
-  float* __restrict__ gb = gv + voff;
-  const T* zp = reinterpret_cast<const T*>(g_zero_line);
-
-  LevelTable lt;
-  lt.load(shapes, start, L, lane);
-
-  float go[VEC];
-  Vec16<T>::unpack(ldg128(grad_out + u * D + cl * VEC), go);
-
-  for (int s0 = g; s0 < LP + g; s0 += G * U) {
-    float lx[U], ly[U], a[U];
-    int sc[U];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const int s = s0 + j * G;
-      sc[j] = s < LP ? s : -1;
-      const int si = s < LP ? s : 0;
-      load_xy(u_loc + 2 * si, lx[j], ly[j]);
-      a[j] = load_s(u_att + si);
-    }
-    Geo<float> ge[U];
-    long long row[U];
-    int Hs[U];
-    const T* tp[U][4];
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      const bool valid = sc[j] >= 0;
-      const int l = valid ? level_of(sc[j], inv_p) : 0;
-      Hs[j] = __shfl_sync(0xffffffffu, lt.H, l);
-      const int W = __shfl_sync(0xffffffffu, lt.W, l);
-      const int st = __shfl_sync(0xffffffffu, lt.st, l);
-      ge[j] = make_geo<float>(lx[j], ly[j], Hs[j], W, valid);
-      row[j] = ((long long)st + ge[j].row00) * MD;
-      const T* t0 = vb + row[j];
-      const int rs = W * MD;
-      tp[j][0] = ge[j].ok00 ? t0 : zp;
-      tp[j][1] = ge[j].ok01 ? t0 + MD : zp;
-      tp[j][2] = ge[j].ok10 ? t0 + rs : zp;
-      tp[j][3] = ge[j].ok11 ? t0 + rs + MD : zp;
-    }
-    uint4 v[U][4];
-#pragma unroll
-    for (int j = 0; j < U; ++j)
-#pragma unroll
-      for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
-#pragma unroll
-    for (int j = 0; j < U; ++j) {
-      float f00[VEC], f01[VEC], f10[VEC], f11[VEC];
-      Vec16<T>::unpack(v[j][0], f00);
-      Vec16<T>::unpack(v[j][1], f01);
-      Vec16<T>::unpack(v[j][2], f10);
-      Vec16<T>::unpack(v[j][3], f11);
-      const float hy = ge[j].hy, hx = ge[j].hx, ly_ = ge[j].ly, lx_ = ge[j].lx;
-      float s_a = 0.f, s_x = 0.f, s_y = 0.f;
-#pragma unroll
-      for (int i = 0; i < VEC; ++i) {
-        const float top = hx * f00[i] + lx_ * f01[i];  // interpolated along x on row y0
-        const float bot = hx * f10[i] + lx_ * f11[i];  // ... on row y0+1
-        s_a = fmaf(go[i], hy * top + ly_ * bot, s_a);
-        s_y = fmaf(go[i], bot - top, s_y);
-        s_x = fmaf(go[i], hy * (f01[i] - f00[i]) + ly_ * (f11[i] - f10[i]), s_x);
-      }
-      {  // scatter into grad_value: bilinear weight * attention * grad_out
-        float* g0 = gb + row[j];
-        const int rs = ge[j].W * MD;
-        const float w00 = hy * hx * a[j], w01 = hy * lx_ * a[j], w10 = ly_ * hx * a[j], w11 = ly_ * lx_ * a[j];
-#pragma unroll
-        for (int i = 0; i < VEC; i += 4) {
-          if (ge[j].ok00) red_add_v4(g0 + i, w00 * go[i], w00 * go[i + 1], w00 * go[i + 2], w00 * go[i + 3]);
-          if (ge[j].ok01) red_add_v4(g0 + MD + i, w01 * go[i], w01 * go[i + 1], w01 * go[i + 2], w01 * go[i + 3]);
-          if (ge[j].ok10) red_add_v4(g0 + rs + i, w10 * go[i], w10 * go[i + 1], w10 * go[i + 2], w10 * go[i + 3]);
-          if (ge[j].ok11) red_add_v4(g0 + rs + MD + i, w11 * go[i], w11 * go[i + 1], w11 * go[i + 2], w11 * go[i + 3]);
-        }
-      }
-#pragma unroll
-      for (int off = 1; off < LPR; off <<= 1) {  // channel sums over the LPR lanes of this group
-        s_a += __shfl_xor_sync(0xffffffffu, s_a, off);
-        s_x += __shfl_xor_sync(0xffffffffu, s_x, off);
-        s_y += __shfl_xor_sync(0xffffffffu, s_y, off);
-      }
-      if (cl == 0 && sc[j] >= 0) {
-        const long long sidx = u * LP + sc[j];
-        gattn[sidx] = from_acc<T>(s_a);
-        T* gl = gloc + 2 * sidx;
-        gl[0] = from_acc<T>((float)ge[j].W * a[j] * s_x);
-        gl[1] = from_acc<T>((float)Hs[j] * a[j] * s_y);
-      }
-    }
-  }
-}
-
-// ------------------------------------------------------------------------------------------------
-// VECTOR kernels, "sample-geometry" variant (default)
-// ------------------------------------------------------------------------------------------------
-// In the kernels above all LPR lanes of a group redo the coordinate -> tap-address arithmetic of their
-// sample (~55 instructions), so a (b,q,m) unit with 16 samples costs ~600 warp instructions and the SMs are
-// issue-bound for a good part of the run.  Here lane i of the warp does that arithmetic ONCE for sample i
-// (one coalesced read of the unit's 128-byte location block, 64-byte weight block), and the lane groups
-// fetch {tap offset, row stride | validity bits, 4 weights} of the sample they gather with warp shuffles.
-// Offsets are 32-bit (host checks S*M*D <= 2^27).  Grid: x = units of one image, y = image.
 struct SampleGeo {
-  int off00;   // element offset of tap (y0, x0) from the image base (head/channel offset NOT included)
-  int rsf;     // (W * M * D) << 4 | ok11 << 3 | ok10 << 2 | ok01 << 1 | ok00
+  int off00;  // element offset of tap (y0, x0) from the image base (head / channel offset NOT included)
+  int rsf;    // (W * M * D) << 4 | ok11 << 3 | ok10 << 2 | ok01 << 1 | ok00
 };
 
 template <typename T>
@@ -436,33 +220,56 @@ __device__ __forceinline__ void sample_geometry(const T* __restrict__ u_loc, con
   sg.rsf = ((W * MD) << 4) | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
 }
 
-template <typename T, int D, int U>
+// the four tap pointers of one sample; `all_ok` is warp-uniform
+template <typename T>
+__device__ __forceinline__ void tap_pointers(const T* vb, int off, int rsf, int MD, bool all_ok, const T* (&tp)[4]) {
+  const T* t0 = vb + off;
+  const T* t1 = t0 + (rsf >> 4);
+  if (all_ok) {
+    tp[0] = t0; tp[1] = t0 + MD; tp[2] = t1; tp[3] = t1 + MD;
+  } else {
+    const T* zp = reinterpret_cast<const T*>(g_zero_line);
+    tp[0] = (rsf & 1) ? t0 : zp;
+    tp[1] = (rsf & 2) ? t0 + MD : zp;
+    tp[2] = (rsf & 4) ? t1 : zp;
+    tp[3] = (rsf & 8) ? t1 + MD : zp;
+  }
+}
+
+// packed fp32 pairs (sm_100 FFMA2 / FMUL2: two lanes of fp32 math per issue slot)
+__device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return __ffma2_rn(make_float2(w, w), v, acc); }
+
+// ------------------------------------------------------------------------------------------------
+// VECTOR FORWARD
+// ------------------------------------------------------------------------------------------------
+// Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
+template <typename T, int D, int MC, int U>
 __global__ void __launch_bounds__(MSDA_MAX_THREADS)
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int M, int L, int P, float inv_p, int QM) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
 
+  const int M = MC > 0 ? MC : Mrt;
+  const int MD = M * D;
   const int lane = threadIdx.x & 31;
   const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // unit inside image blockIdx.y
   if (uq >= QM) return;                                                // warp-uniform
   const int g = lane / LPR, cl = lane % LPR;
   const int m = uq % M;
   const int LP = L * P;
-  const int MD = M * D;
   const long long u = (long long)blockIdx.y * QM + uq;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
+  const T* __restrict__ u_loc = loc + u * (LP * 2);
   const T* __restrict__ u_att = attn + u * LP;
-  const T* __restrict__ vb = value + (long long)blockIdx.y * S * MD + m * D + cl * VEC;
-  const T* zp = reinterpret_cast<const T*>(g_zero_line);
+  const T* __restrict__ vb = value + (long long)blockIdx.y * S * MD + (m * D + cl * VEC);
 
-  float acc[VEC];
+  float2 acc[VEC / 2];
 #pragma unroll
-  for (int i = 0; i < VEC; ++i) acc[i] = 0.f;
+  for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 
   for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane
     SampleGeo sg;
@@ -473,25 +280,25 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
     for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
-      const T* tp[U][4];
+      int off[U], rsf[U];
       float w[U][4];
+      bool full = true;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int src = k0 + j * G + g;
-        const int off = __shfl_sync(0xffffffffu, sg.off00, src);
-        int rsf = __shfl_sync(0xffffffffu, sg.rsf, src);
+        off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
+        rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
         w[j][0] = __shfl_sync(0xffffffffu, w00, src);
         w[j][1] = __shfl_sync(0xffffffffu, w01, src);
         w[j][2] = __shfl_sync(0xffffffffu, w10, src);
         w[j][3] = __shfl_sync(0xffffffffu, w11, src);
-        if (src >= cnt) rsf = 0;  // shfl wraps modulo 32: a lane group past the end must not gather
-        const T* t0 = vb + off;
-        const int rs = rsf >> 4;
-        tp[j][0] = (rsf & 1) ? t0 : zp;
-        tp[j][1] = (rsf & 2) ? t0 + MD : zp;
-        tp[j][2] = (rsf & 4) ? t0 + rs : zp;
-        tp[j][3] = (rsf & 8) ? t0 + rs + MD : zp;
+        if (src >= cnt) rsf[j] = 0;  // shfl wraps modulo 32: a lane group past the end must not gather
+        full = full && ((rsf[j] & 15) == 15);
       }
+      const bool all_ok = __all_sync(0xffffffffu, full);
+      const T* tp[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j) tap_pointers<T>(vb, off[j], rsf[j], MD, all_ok, tp[j]);
       uint4 v[U][4];
 #pragma unroll
       for (int j = 0; j < U; ++j)
@@ -504,47 +311,65 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
           float f[VEC];
           Vec16<T>::unpack(v[j][t], f);
 #pragma unroll
-          for (int i = 0; i < VEC; ++i) acc[i] = fmaf(w[j][t], f[i], acc[i]);
+          for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
         }
     }
   }
+  float r[VEC];
 #pragma unroll
-  for (int off = LPR; off < 32; off <<= 1)
+  for (int i = 0; i < VEC / 2; ++i) { r[2 * i] = acc[i].x; r[2 * i + 1] = acc[i].y; }
 #pragma unroll
-    for (int i = 0; i < VEC; ++i) acc[i] += __shfl_xor_sync(0xffffffffu, acc[i], off);
-  if (g == 0) *reinterpret_cast<uint4*>(out + u * D + cl * VEC) = Vec16<T>::pack(acc);
+  for (int o = LPR; o < 32; o <<= 1)
+#pragma unroll
+    for (int i = 0; i < VEC; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
+  if (g == 0) *reinterpret_cast<uint4*>(out + u * D + cl * VEC) = Vec16<T>::pack(r);
 }
 
-template <typename T, int D, int U>
+// ------------------------------------------------------------------------------------------------
+// VECTOR BACKWARD
+// ------------------------------------------------------------------------------------------------
+// grad_value accumulates in fp32 (`gv`): the caller's tensor for T=float, a workspace for 16-bit T.
+//
+// Two passes, split by a programmatic-dependent-launch fence:
+//   pass 1  gathers the taps, forms per sample the four dot products <grad_out, tap> over the channels,
+//           reduces them across the LPR lanes, hands them back to the lane that owns the sample, which
+//           combines them into grad_attn / grad_loc and writes those coalesced.  Touches neither grad_value
+//           nor anything the preceding zero-fill kernel writes, so it runs CONCURRENTLY with that kernel
+//           (the fill triggers `griddepcontrol.launch_dependents` at its start);
+//   fence   `griddepcontrol.wait`: the zero-fill has completed and is visible;
+//   pass 2  recomputes the (cheap) geometry and scatters weight * attention * grad_out into grad_value with
+//           16-byte `red.global.add.v4.f32` (no return value, resolved in L2).
+template <typename T, int D, int MC, int U>
 __global__ void __launch_bounds__(MSDA_MAX_THREADS)
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
                    T* __restrict__ gloc, T* __restrict__ gattn,
-                   int S, int M, int L, int P, float inv_p, int QM) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
 
+  const int M = MC > 0 ? MC : Mrt;
+  const int MD = M * D;
   const int lane = threadIdx.x & 31;
   const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (uq >= QM) return;
+  if (uq >= QM) return;  // warp-uniform (an exited warp needs no fence)
   const int g = lane / LPR, cl = lane % LPR;
   const int m = uq % M;
   const int LP = L * P;
-  const int MD = M * D;
   const long long u = (long long)blockIdx.y * QM + uq;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
+  const T* __restrict__ u_loc = loc + u * (LP * 2);
   const T* __restrict__ u_att = attn + u * LP;
-  const long long voff = (long long)blockIdx.y * S * MD + m * D + cl * VEC;
+  const long long voff = (long long)blockIdx.y * S * MD + (m * D + cl * VEC);
   const T* __restrict__ vb = value + voff;
   float* __restrict__ gb = gv + voff;
-  const T* zp = reinterpret_cast<const T*>(g_zero_line);
 
   float go[VEC];
   Vec16<T>::unpack(ldg128(grad_out + u * D + cl * VEC), go);
 
+  // ---------------- pass 1: grad_attn, grad_loc ----------------
   for (int base = 0; base < LP; base += 32) {
     SampleGeo sg;
     Geo<float> ge;
@@ -553,27 +378,22 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
     const bool have = base + lane < LP;
     sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, MD, sg, ge, a, H, W);
     const int cnt = min(32, LP - base);
-    float r_a = 0.f, r_x = 0.f, r_y = 0.f;  // channel sums of MY sample, collected from the group that gathered it
+    float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;  // <grad_out, tap> of MY sample, from the group that gathered it
     for (int k0 = 0; k0 < cnt; k0 += G * U) {
-      const T* tp[U][4];
       int off[U], rsf[U];
-      float fly[U], flx[U], fa[U];
+      bool full = true;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int src = k0 + j * G + g;
         off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
         rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
-        fly[j] = __shfl_sync(0xffffffffu, ge.ly, src);
-        flx[j] = __shfl_sync(0xffffffffu, ge.lx, src);
-        fa[j] = __shfl_sync(0xffffffffu, a, src);
         if (src >= cnt) rsf[j] = 0;
-        const T* t0 = vb + off[j];
-        const int rs = rsf[j] >> 4;
-        tp[j][0] = (rsf[j] & 1) ? t0 : zp;
-        tp[j][1] = (rsf[j] & 2) ? t0 + MD : zp;
-        tp[j][2] = (rsf[j] & 4) ? t0 + rs : zp;
-        tp[j][3] = (rsf[j] & 8) ? t0 + rs + MD : zp;
+        full = full && ((rsf[j] & 15) == 15);
       }
+      const bool all_ok = __all_sync(0xffffffffu, full);
+      const T* tp[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j) tap_pointers<T>(vb, off[j], rsf[j], MD, all_ok, tp[j]);
       uint4 v[U][4];
 #pragma unroll
       for (int j = 0; j < U; ++j)
@@ -581,52 +401,76 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        float f00[VEC], f01[VEC], f10[VEC], f11[VEC];
-        Vec16<T>::unpack(v[j][0], f00);
-        Vec16<T>::unpack(v[j][1], f01);
-        Vec16<T>::unpack(v[j][2], f10);
-        Vec16<T>::unpack(v[j][3], f11);
-        const float ly_ = fly[j], lx_ = flx[j], hy = 1.f - ly_, hx = 1.f - lx_;
-        float s_a = 0.f, s_x = 0.f, s_y = 0.f;
+        float d[4];
 #pragma unroll
-        for (int i = 0; i < VEC; ++i) {
-          const float top = hx * f00[i] + lx_ * f01[i];  // interpolated along x on row y0
-          const float bot = hx * f10[i] + lx_ * f11[i];  // ... on row y0+1
-          s_a = fmaf(go[i], hy * top + ly_ * bot, s_a);
-          s_y = fmaf(go[i], bot - top, s_y);
-          s_x = fmaf(go[i], hy * (f01[i] - f00[i]) + ly_ * (f11[i] - f10[i]), s_x);
-        }
-        {  // scatter into grad_value: bilinear weight * attention * grad_out
-          float* g0 = gb + off[j];
-          const int rs = rsf[j] >> 4;
-          const float w00 = hy * hx * fa[j], w01 = hy * lx_ * fa[j], w10 = ly_ * hx * fa[j], w11 = ly_ * lx_ * fa[j];
+        for (int t = 0; t < 4; ++t) {
+          float f[VEC];
+          Vec16<T>::unpack(v[j][t], f);
+          float2 p = make_float2(0.f, 0.f);
 #pragma unroll
-          for (int i = 0; i < VEC; i += 4) {
-            if (rsf[j] & 1) red_add_v4(g0 + i, w00 * go[i], w00 * go[i + 1], w00 * go[i + 2], w00 * go[i + 3]);
-            if (rsf[j] & 2) red_add_v4(g0 + MD + i, w01 * go[i], w01 * go[i + 1], w01 * go[i + 2], w01 * go[i + 3]);
-            if (rsf[j] & 4) red_add_v4(g0 + rs + i, w10 * go[i], w10 * go[i + 1], w10 * go[i + 2], w10 * go[i + 3]);
-            if (rsf[j] & 8) red_add_v4(g0 + rs + MD + i, w11 * go[i], w11 * go[i + 1], w11 * go[i + 2], w11 * go[i + 3]);
-          }
+          for (int i = 0; i < VEC / 2; ++i) p = __ffma2_rn(make_float2(go[2 * i], go[2 * i + 1]), make_float2(f[2 * i], f[2 * i + 1]), p);
+          d[t] = p.x + p.y;
         }
 #pragma unroll
-        for (int o = 1; o < LPR; o <<= 1) {  // channel sums over the LPR lanes of this group
-          s_a += __shfl_xor_sync(0xffffffffu, s_a, o);
-          s_x += __shfl_xor_sync(0xffffffffu, s_x, o);
-          s_y += __shfl_xor_sync(0xffffffffu, s_y, o);
-        }
+        for (int o = 1; o < LPR; o <<= 1)  // channel sums over the LPR lanes of this group
+#pragma unroll
+          for (int t = 0; t < 4; ++t) d[t] += __shfl_xor_sync(0xffffffffu, d[t], o);
         // hand the sums back to the lane that owns the sample: lane (k0 + j*G + g') reads from group g'
         const int rel = lane - k0 - j * G;
         const int from = (rel & (G - 1)) * LPR;
-        const float t_a = __shfl_sync(0xffffffffu, s_a, from);
-        const float t_x = __shfl_sync(0xffffffffu, s_x, from);
-        const float t_y = __shfl_sync(0xffffffffu, s_y, from);
-        if (rel >= 0 && rel < G) { r_a = t_a; r_x = t_x; r_y = t_y; }
+        const float t00 = __shfl_sync(0xffffffffu, d[0], from);
+        const float t01 = __shfl_sync(0xffffffffu, d[1], from);
+        const float t10 = __shfl_sync(0xffffffffu, d[2], from);
+        const float t11 = __shfl_sync(0xffffffffu, d[3], from);
+        if (rel >= 0 && rel < G) { r00 = t00; r01 = t01; r10 = t10; r11 = t11; }
       }
     }
     if (have) {  // coalesced: 32 consecutive samples of the unit
+      const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
+      const float bot = ge.hx * r10 + ge.lx * r11;  // ... on row y0 + 1
       const long long sidx = u * LP + base + lane;
-      gattn[sidx] = from_acc<T>(r_a);
-      store_xy(gloc + 2 * sidx, (float)W * a * r_x, (float)H * a * r_y);
+      gattn[sidx] = from_acc<T>(ge.hy * top + ge.ly * bot);
+      const float gx = ge.hy * (r01 - r00) + ge.ly * (r11 - r10);
+      const float gy = bot - top;
+      store_xy(gloc + 2 * sidx, (float)W * a * gx, (float)H * a * gy);
+    }
+  }
+
+  // ---------------- fence: the zero-fill of grad_value (previous kernel in the stream) is complete ----------------
+  asm volatile("griddepcontrol.wait;" ::: "memory");
+
+  // ---------------- pass 2: scatter into grad_value ----------------
+  for (int base = 0; base < LP; base += 32) {
+    SampleGeo sg;
+    Geo<float> ge;
+    float a;
+    int H, W;
+    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, base + lane < LP, inv_p, MD, sg, ge, a, H, W);
+    const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
+    const int cnt = min(32, LP - base);
+    for (int k0 = 0; k0 < cnt; k0 += G) {
+      const int src = k0 + g;
+      const int off = __shfl_sync(0xffffffffu, sg.off00, src);
+      int rsf = __shfl_sync(0xffffffffu, sg.rsf, src);
+      float w[4];
+      w[0] = __shfl_sync(0xffffffffu, w00, src);
+      w[1] = __shfl_sync(0xffffffffu, w01, src);
+      w[2] = __shfl_sync(0xffffffffu, w10, src);
+      w[3] = __shfl_sync(0xffffffffu, w11, src);
+      if (src >= cnt) rsf = 0;
+      float* g0 = gb + off;
+      float* g1 = g0 + (rsf >> 4);
+      float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
+#pragma unroll
+      for (int t = 0; t < 4; ++t)
+        if (rsf & (1 << t)) {
+#pragma unroll
+          for (int i = 0; i < VEC; i += 4) {
+            const float2 lo = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i], go[i + 1]));
+            const float2 hi = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i + 2], go[i + 3]));
+            red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
+          }
+        }
     }
   }
 }
@@ -742,6 +586,8 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
 // helpers: zero fill (128-bit stores, grid-stride) and fp32 -> 16-bit conversion of grad_value
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msda_zero_kernel(uint4* __restrict__ p, long long n16, unsigned char* __restrict__ tail, int ntail) {
+  // let a programmatically-dependent kernel (the backward gather pass) start while this fill is running
+  asm volatile("griddepcontrol.launch_dependents;");
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;

@@ -206,8 +206,8 @@ def main():
 
     # rotating input sets: total footprint > 2x L2 so that every step reads its inputs from HBM
     step_bytes = w.algorithmic_bytes(elt, False) + w.algorithmic_bytes(elt, True)
-    # (the gather touches only part of each value tensor, so provision ~6x L2 of nominal footprint)
-    n_sets = max(4, int(6 * L2_BYTES / step_bytes) + 2)
+    # (the gather touches only part of each value tensor, so provision ~8x L2 of nominal footprint)
+    n_sets = max(4, int(8 * L2_BYTES / step_bytes) + 2)
     while n_sets * step_bytes > 40e9 and n_sets > 2:
         n_sets -= 1
     sets = [device_inputs(w, seed=1000 * rank + i, device=dev, dtype=tdt, loc_mode=args.loc_mode) for i in range(n_sets)]
@@ -323,7 +323,7 @@ def main():
                 "workload": f"{w.name} per GPU: N={w.N}, levels={[list(l) for l in w.levels]}, Lq={w.Lq}, M={w.M}, "
                             f"P={w.P}, D={w.D}, loc={args.loc_mode}; step = forward + backward",
                 "samples_per_step_per_gpu": w.samples,
-                "l2_policy": f"rotating {n_sets} distinct input sets ({n_sets * step_bytes / 1e6:.0f} MB nominal, >= 6x the 126 MB L2)",
+                "l2_policy": f"rotating {n_sets} distinct input sets ({n_sets * step_bytes / 1e6:.0f} MB nominal, >= 8x the 126 MB L2)",
                 "launch": f"CUDA graph of {chunk} steps x {reps} replays",
                 "sharding": "batch-sharded, no data-path collective",
             },

@@ -21,7 +21,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _ops(cuda_device):
     msda.load_ops()
-    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "variant"):
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -124,13 +124,13 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 
 
 @pytest.mark.parametrize("w", [SHAPES[0], SHAPES[1], SHAPES[9]], ids=lambda w: w.name)
-@pytest.mark.parametrize("variant", [0, 1])
+@pytest.mark.parametrize("no_pdl", [0, 1])
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
                                       ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8)])
-def test_kernel_variants_agree(knob, val, variant, w, cuda_device):
+def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)
-    _capi.set_tuning("variant", variant)
+    _capi.set_tuning("no_pdl", no_pdl)
     _capi.set_tuning(knob, val)
     got = run_op(x, cuda_device)
     assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
