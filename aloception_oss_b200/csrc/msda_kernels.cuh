@@ -53,18 +53,15 @@ struct Geo {
   bool ok00, ok01, ok10, ok11;  // tap inside the level AND sample inside the window
 };
 
-__device__ __forceinline__ float mul_rn(float a, float b) { return __fmul_rn(a, b); }
-__device__ __forceinline__ double mul_rn(double a, double b) { return __dmul_rn(a, b); }
-__device__ __forceinline__ float sub_rn(float a, float b) { return __fsub_rn(a, b); }
-__device__ __forceinline__ double sub_rn(double a, double b) { return __dsub_rn(a, b); }
-
 // `valid` = this lane group really has a sample (tail predicate).
 template <typename A>
 __device__ __forceinline__ Geo<A> make_geo(A loc_x, A loc_y, int H, int W, bool valid) {
   Geo<A> g;
-  // separate multiply and subtract (no FMA contraction) = the reference's rounding of the coordinate
-  const A y = sub_rn(mul_rn(loc_y, (A)H), (A)0.5);
-  const A x = sub_rn(mul_rn(loc_x, (A)W), (A)0.5);
+  // ONE rounding (fused multiply-add): this is what the reference's `loc * size - 0.5` compiles to with nvcc's
+  // default -fmad=true (verified on the B200: tools/debug_gradloc.py), and it is the closest fp32 gets to the
+  // exact coordinate -- floor() decides which pixel pair is interpolated, and grad_loc jumps across that decision.
+  const A y = fma(loc_y, (A)H, (A)-0.5);
+  const A x = fma(loc_x, (A)W, (A)-0.5);
   const bool inside = valid && y > (A)-1 && x > (A)-1 && y < (A)H && x < (A)W;
   const A fy = floor(y), fx = floor(x);
   const int y0 = (int)fy, x0 = (int)fx;

@@ -77,3 +77,28 @@ def check_grad_value(gv, ref, rtol, atol=None, what="grad_value"):
     assert_close(gv.sum(-1), ref["gv_sum_channels"], rtol, atol * D, what + ".sum(channels)")
     assert_close(gv.sum(1), ref["gv_sum_pixels"], rtol, atol * np.sqrt(S) * 4, what + ".sum(pixels)")
     assert_close(gv.reshape(-1)[ref["gv_pick_idx"]], ref["gv_pick_val"], rtol, atol, what + "[picked]")
+
+
+def near_floor_discontinuity(loc, shapes, eps=2e-5):
+    """Mask (N, Lq, M, L, P) of samples whose pixel coordinate is within ``eps`` of an integer.
+
+    grad_loc is DISCONTINUOUS there (floor() switches the interpolated pixel pair), so two correct evaluations
+    that round ``loc * size - 0.5`` differently (fp32 FMA vs fp32 mul+sub vs fp64) legitimately disagree on
+    grad_loc for such a sample -- the reference's own CUDA fp32 kernel and its fp64 evaluation do
+    (tools/debug_gradloc.py).  out, grad_value and grad_attn are continuous and are never masked.
+    """
+    loc = np.asarray(loc, dtype=np.float64)
+    shapes = np.asarray(shapes, dtype=np.float64)
+    wh = shapes[:, ::-1].reshape(1, 1, 1, -1, 1, 2)  # (W, H) per level, matching (x, y)
+    pix = loc * wh - 0.5
+    return (np.abs(pix - np.round(pix)) < eps).any(-1)
+
+
+def assert_close_grad_loc(got, want, loc, shapes, rtol=1e-4, what="grad_loc"):
+    """grad_loc check that skips the (measure-zero) samples sitting on a floor() discontinuity."""
+    got = np.asarray(got, dtype=np.float64).copy()
+    want = np.asarray(want, dtype=np.float64)
+    skip = near_floor_discontinuity(loc, shapes)
+    assert skip.mean() < 1e-2, "too many samples masked"
+    got[skip] = want[skip]
+    assert_close(got, want, rtol, rtol * rms(want), what)

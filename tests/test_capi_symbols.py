@@ -1,0 +1,64 @@
+"""The C-ABI library loads and exports every symbol include/msda_b200.h declares (no compute: no GPU here)."""
+import ctypes
+import os
+import re
+
+from aloception_oss_b200 import _capi
+
+HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "include", "msda_b200.h")
+
+
+def declared_functions():
+    txt = open(HEADER).read()
+    txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
+    return sorted(set(re.findall(r"\b(msda_[a-z_]+)\s*\(", txt)))
+
+
+def test_header_declares_the_expected_entry_points():
+    names = declared_functions()
+    for n in ("msda_forward", "msda_backward", "msda_backward_workspace_bytes", "msda_forward_host", "msda_version",
+              "msda_last_error_string", "msda_set_tuning", "msda_get_tuning", "msda_kernel_launch_count"):
+        assert n in names
+
+
+def test_library_exports_every_declared_symbol():
+    _capi.build_library()
+    lib = ctypes.CDLL(_capi.LIB_PATH)
+    for name in declared_functions():
+        assert hasattr(lib, name), f"{name} declared in msda_b200.h but not exported by libmsda_b200.so"
+
+
+def test_abi_version_and_error_channel():
+    lib = _capi.lib()
+    assert lib.msda_version() == _capi.ABI_VERSION
+    assert _capi.last_error() == ""
+    # argument validation happens before any CUDA call, so it is testable without a device
+    dims = _capi.MsdaDims(1, 4, 1, 32, 1, 1, 1)
+    rc = lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), 99, None)
+    assert rc != 0 and "unknown dtype" in _capi.last_error()
+    dims = _capi.MsdaDims(1, 4, 1, 32, 1, -1, 1)
+    rc = lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), _capi.F32, None)
+    assert rc != 0 and "negative dimension" in _capi.last_error()
+    dims = _capi.MsdaDims(1, 4, 1, 32, 1, 1, 1)
+    rc = lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), _capi.F32, None)
+    assert rc != 0 and "NULL" in _capi.last_error()
+    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.BF16, 0, None)
+    assert rc != 0 and "workspace too small" in _capi.last_error()
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.BF16) == 4 * 4 * 32
+    assert lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.F32) == 0
+    # empty problems succeed without touching the device
+    dims = _capi.MsdaDims(0, 4, 1, 32, 1, 1, 1)
+    assert lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), _capi.F32, None) == 0
+
+
+def test_tuning_knobs_roundtrip():
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl"):
+        _capi.set_tuning(k, 3)
+        assert _capi.get_tuning(k) == 3
+        _capi.set_tuning(k, 0)
+    try:
+        _capi.set_tuning("no_such_knob", 1)
+    except ValueError as e:
+        assert "unknown tuning knob" in str(e)
+    else:
+        raise AssertionError("unknown knob accepted")

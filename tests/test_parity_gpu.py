@@ -13,7 +13,8 @@ import aloception_oss_b200 as msda
 from aloception_oss_b200 import _capi
 from aloception_oss_b200.synthetic import WORKLOADS, Workload, device_inputs, torch_inputs
 from oracle import msda_oracle
-from tests._util import assert_close, assert_close_grad, check_grad_value, golden_names, load_golden, rms
+from tests._util import (assert_close, assert_close_grad, assert_close_grad_loc, check_grad_value, golden_names,
+                         load_golden, rms)
 
 pytestmark = pytest.mark.gpu
 
@@ -66,7 +67,7 @@ def test_golden(name, cuda_device):
         check_grad_value(gv, ref, 1e-9, 1e-14)
     else:
         assert_close(out, ref["out64"], 1e-4, 1e-4 * 1e-3 * rms(ref["out64"]), "out")
-        assert_close_grad(gl, ref["grad_loc64"], 1e-4, "grad_loc")
+        assert_close_grad_loc(gl, ref["grad_loc64"], x["loc"], x["shapes"], 1e-4)
         assert_close_grad(ga, ref["grad_attn64"], 1e-4, "grad_attn")
         check_grad_value(gv, ref, 1e-4)
 
@@ -96,7 +97,7 @@ def test_fp32_vs_oracle(w, mode, cuda_device):
     want = oracle64(x)
     assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
     check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
-    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad_loc(got[2], want[2], x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
     assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
 
 
@@ -135,7 +136,7 @@ def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     got = run_op(x, cuda_device)
     assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
     check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
-    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad_loc(got[2], want[2], x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
     assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
 
 
@@ -250,7 +251,7 @@ def test_c2_against_oracle_full(cuda_device):
     want = oracle64(x)
     assert_close(got[0], want[0], 1e-4, 1e-7 * rms(want[0]), "out")
     check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
-    assert_close_grad(got[2], want[2], 1e-4, "grad_loc")
+    assert_close_grad_loc(got[2], want[2], x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
     assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
 
 
