@@ -68,7 +68,7 @@ struct Launch {
 // one warp per (b, q, m) unit
 Launch unit_launch(long long units, int default_warps) {
   int wpb = g_warps_per_block.load(std::memory_order_relaxed);
-  if (wpb <= 0 || wpb > MSDA_MAX_THREADS / 32) wpb = default_warps;
+  if (wpb <= 0 || wpb > 8) wpb = default_warps;
   Launch l;
   l.block = dim3(32 * wpb);
   l.grid = dim3((unsigned)((units + wpb - 1) / wpb));

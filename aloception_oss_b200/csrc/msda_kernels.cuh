@@ -20,7 +20,7 @@
 #include <stdint.h>
 
 #ifndef MSDA_MAX_THREADS
-#define MSDA_MAX_THREADS 256  // warps_per_block <= 8: leaves ptxas the register room for 16 x 128-bit loads in flight
+#define MSDA_MAX_THREADS 128  // warps_per_block <= 4 (2 is the default: small CTAs fill the SMs evenly)
 #endif
 
 namespace msda {
@@ -240,8 +240,10 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // VECTOR FORWARD
 // ------------------------------------------------------------------------------------------------
 // Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
+// Register budgets via min-CTAs/SM at 128 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 56 regs (36 warps/SM, keeps the
+// 4 800-unit C2 call in ONE wave), U=4 -> 80 regs (24 warps/SM).
 template <typename T, int D, int MC, int U>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 12 : (U == 2 ? 9 : 6))
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
@@ -337,7 +339,7 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 //   pass 2  recomputes the (cheap) geometry and scatters weight * attention * grad_out into grad_value with
 //           16-byte `red.global.add.v4.f32` (no return value, resolved in L2).
 template <typename T, int D, int MC, int U>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 10 : (U == 2 ? 9 : 6))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
@@ -476,7 +478,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
 // GENERIC kernels: any D, L, P; T in {float, double, bf16, half}.  Warp per unit, lanes over channels.
 // ------------------------------------------------------------------------------------------------
 template <typename T>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+__global__ void __launch_bounds__(256)
 msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                         const int32_t* __restrict__ start, const T* __restrict__ loc,
                         const T* __restrict__ attn, T* __restrict__ out,
@@ -518,7 +520,7 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__
 }
 
 template <typename T>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS)
+__global__ void __launch_bounds__(256)
 msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                         const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                         const T* __restrict__ loc, const T* __restrict__ attn,

@@ -89,12 +89,21 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t.numel() else ctypes.c_void_p(0)
 
 
-def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64):
-    """CUDA forward: (N,S,M,D), (L,2) i32, (L,) i32, (N,Lq,M,L,P,2), (N,Lq,M,L,P) -> (N, Lq, M*D)."""
+def _check_out(t, shape, like, name):
+    if tuple(t.shape) != tuple(shape) or t.dtype != like.dtype or t.device != like.device or not t.is_contiguous():
+        raise RuntimeError(f"{name} must be a contiguous {like.dtype} tensor of shape {tuple(shape)} on {like.device}")
+    return t
+
+
+def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step=64, out=None):
+    """CUDA forward: (N,S,M,D), (L,2) i32, (L,) i32, (N,Lq,M,L,P,2), (N,Lq,M,L,P) -> (N, Lq, M*D).
+
+    ``out`` (optional) is a caller-provided result buffer, e.g. a view into a packed staging arena."""
     dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
-    out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=value.device)
+    oshape = (dims.batch, dims.num_query, dims.num_heads * dims.channels)
+    out = torch.empty(oshape, dtype=value.dtype, device=value.device) if out is None else _check_out(out, oshape, value, "out")
     with torch.cuda.device(value.device):
         stream = torch.cuda.current_stream().cuda_stream
         rc = _capi.lib().msda_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight),
@@ -105,17 +114,22 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step=64):
-    """CUDA backward -> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:83-153)."""
+                            im2col_step=64, grads=None):
+    """CUDA backward -> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:83-153).
+
+    ``grads`` (optional): three caller-provided result buffers shaped like value / sampling_loc / attn_weight."""
     dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
                           extra=(("grad_output", grad_output),))
     if grad_output.numel() != dims.batch * dims.num_query * dims.num_heads * dims.channels:
         raise RuntimeError(f"grad_output {tuple(grad_output.shape)} does not match the forward output")
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
-    grad_value = torch.empty_like(value)
-    grad_loc = torch.empty_like(sampling_loc)
-    grad_attn = torch.empty_like(attn_weight)
+    if grads is None:
+        grad_value, grad_loc, grad_attn = torch.empty_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+    else:
+        grad_value = _check_out(grads[0], value.shape, value, "grads[0]")
+        grad_loc = _check_out(grads[1], sampling_loc.shape, value, "grads[1]")
+        grad_attn = _check_out(grads[2], attn_weight.shape, value, "grads[2]")
     L = _capi.lib()
     dt = _DTYPES[value.dtype]
     ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)

@@ -344,53 +344,79 @@ def main():
 
 def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
     """Same step through the public API with HOST buffers: every step uploads its inputs from pinned memory and
-    downloads out + the three gradients.  3-stage pipeline (upload / compute / download streams)."""
+    downloads out + the three gradients.  Inputs and results live in packed arenas (one H2D and one D2H copy per
+    step); 3-slot pipeline on upload / compute / download streams."""
     names = ("value", "loc", "attn", "grad_out")
+    dt = sets[0]["value"].dtype
+    esz = sets[0]["value"].element_size()
+
+    def layout(shapes):
+        offs, off = [], 0
+        for shp in shapes:
+            n = 1
+            for d in shp:
+                n *= d
+            offs.append((off, n, shp))
+            off += (n * esz + 255) // 256 * 256 // esz
+        return offs, off
+
+    in_shapes = [tuple(sets[0][k].shape) for k in names]
+    out_shapes = [(w.N, w.Lq, w.M * w.D), (w.N, w.S, w.M, w.D), (w.N, w.Lq, w.M, w.L, w.P, 2), (w.N, w.Lq, w.M, w.L, w.P)]
+    in_lay, in_total = layout(in_shapes)
+    out_lay, out_total = layout(out_shapes)
+
+    def views(arena, lay):
+        return [arena[o:o + n].view(shp) for o, n, shp in lay]
+
     n_host = min(len(sets), 4)
-    host = [{k: sets[i][k].cpu().pin_memory() for k in names} for i in range(n_host)]
+    host_in = []
+    for i in range(n_host):
+        arena = torch.empty(in_total, dtype=dt).pin_memory()
+        for v, k in zip(views(arena, in_lay), names):
+            v.copy_(sets[i][k])
+        host_in.append(arena)
     depth = 3
     slots = []
     for _ in range(depth):
-        s0 = sets[0]
-        slots.append({
-            "in": {k: torch.empty_like(s0[k]) for k in names},
-            "out_h": None, "ev_up": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_down": torch.cuda.Event(),
-        })
+        d_in = torch.empty(in_total, dtype=dt, device=dev)
+        d_out = torch.empty(out_total, dtype=dt, device=dev)
+        slots.append({"d_in": d_in, "in": dict(zip(names, views(d_in, in_lay))), "d_out": d_out, "out": views(d_out, out_lay),
+                      "h_out": torch.empty(out_total, dtype=dt).pin_memory(),
+                      "ev_up": torch.cuda.Event(), "ev_done": torch.cuda.Event(), "ev_down": torch.cuda.Event()})
     shapes, start = sets[0]["shapes"], sets[0]["start"]
     s_up, s_cp, s_dn = torch.cuda.Stream(dev), torch.cuda.Stream(dev), torch.cuda.Stream(dev)
-    h2d = sum(host[0][k].numel() * host[0][k].element_size() for k in names)
-    out_shapes = [(w.N, w.Lq, w.M * w.D), (w.N, w.S, w.M, w.D), (w.N, w.Lq, w.M, w.L, w.P, 2), (w.N, w.Lq, w.M, w.L, w.P)]
-    for sl in slots:
-        sl["out_h"] = [torch.empty(s, dtype=sets[0]["value"].dtype).pin_memory() for s in out_shapes]
-    d2h = sum(t.numel() * t.element_size() for t in slots[0]["out_h"])
+    h2d = sum(n for _, n, _ in in_lay) * esz
+    d2h = sum(n for _, n, _ in out_lay) * esz
 
     def run(n):
         for i in range(n):
             sl = slots[i % depth]
-            h = host[i % n_host]
             with torch.cuda.stream(s_up):
-                s_up.wait_event(sl["ev_done"])  # slot inputs free once the previous compute on it finished
-                for k in names:
-                    sl["in"][k].copy_(h[k], non_blocking=True)
+                s_up.wait_event(sl["ev_done"])  # slot inputs are free once the previous compute on it finished
+                sl["d_in"].copy_(host_in[i % n_host], non_blocking=True)
                 sl["ev_up"].record(s_up)
             with torch.cuda.stream(s_cp):
                 s_cp.wait_event(sl["ev_up"])
-                x = sl["in"]
-                out = msda.ms_deform_attn_forward(x["value"], shapes, start, x["loc"], x["attn"])
-                gv, gl, ga = msda.ms_deform_attn_backward(x["value"], shapes, start, x["loc"], x["attn"], x["grad_out"])
+                s_cp.wait_event(sl["ev_down"])  # slot outputs are free once their previous download finished
+                x, o = sl["in"], sl["out"]
+                msda.ms_deform_attn_forward(x["value"], shapes, start, x["loc"], x["attn"], out=o[0])
+                msda.ms_deform_attn_backward(x["value"], shapes, start, x["loc"], x["attn"], x["grad_out"], grads=o[1:])
                 sl["ev_done"].record(s_cp)
             with torch.cuda.stream(s_dn):
                 s_dn.wait_event(sl["ev_done"])
-                s_dn.wait_event(sl["ev_down"])
-                for dst, src in zip(sl["out_h"], (out, gv, gl, ga)):
-                    dst.copy_(src, non_blocking=True)
-                    src.record_stream(s_dn)
+                sl["h_out"].copy_(sl["d_out"], non_blocking=True)
                 sl["ev_down"].record(s_dn)
         for s in (s_up, s_cp, s_dn):
             s.synchronize()
 
     run(depth * 2)
     torch.cuda.synchronize()
+    # the pipeline must deliver the operator's results: compare the last download with a direct call
+    last = slots[(depth * 2 - 1) % depth]
+    chk = sets[(depth * 2 - 1) % n_host]
+    ref_out = msda.ms_deform_attn_forward(chk["value"], shapes, start, chk["loc"], chk["attn"])
+    got = views(last["h_out"], out_lay)[0]
+    assert torch.allclose(got, ref_out.cpu(), rtol=1e-5, atol=1e-7), "e2e pipeline returned wrong results"
     if world > 1:
         dist.barrier()
     t0 = time.perf_counter()
@@ -407,7 +433,8 @@ def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
         ms = float(t.item())
     return {"value": w.samples * world / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": K,
-            "path": "pinned host -> H2D -> ms_deform_attn_forward + ms_deform_attn_backward (C ABI) -> D2H of out, grad_value, grad_loc, grad_attn; 3-slot pipeline on 3 streams"}
+            "path": "pinned host arena -> 1 H2D -> ms_deform_attn_forward + ms_deform_attn_backward (C ABI) -> 1 D2H of out, "
+                    "grad_value, grad_loc, grad_attn; 3-slot pipeline on 3 streams; host wall clock"}
 
 
 def run_extra(torch, msda, _capi, dev, tdt, elt, peak):

@@ -105,7 +105,7 @@ int msda_forward_host(const void* value, const int32_t* spatial_shapes, const in
  *   "force_generic"    0|1   route every call through the shape-generic kernels
  *   "fwd_unroll"       0=auto, 1, 2 or 4 samples in flight per lane group in the vector forward kernel
  *   "bwd_unroll"       0=auto, 1, 2 or 4 likewise for the vector backward kernel
- *   "warps_per_block"  0=auto, 1..8
+ *   "warps_per_block"  0=auto, 1..4 (vector kernels), 1..8 (generic kernels)
  *   "no_pdl"           0|1   launch the backward kernel without programmatic dependent launch
  */
 int msda_set_tuning(const char* name, int value);
