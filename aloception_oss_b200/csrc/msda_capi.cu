@@ -78,8 +78,12 @@ Launch unit_launch(long long units, int default_warps) {
 // one warp per unit, grid.y = image (the "sg" kernels use 32-bit in-image indexing)
 Launch image_launch(const msda_dims& d, int default_warps) {
   int wpb = g_warps_per_block.load(std::memory_order_relaxed);
-  if (wpb <= 0 || wpb > MSDA_MAX_THREADS / 32) wpb = default_warps;
   const long long qm = (long long)d.num_query * d.num_heads;
+  if (wpb <= 0 || wpb > MSDA_MAX_THREADS / 32) {
+    // measured (profiles/r1_sweep_tuning.jsonl): calls that fit one wave (<= 36 warps on each of the 148 SMs) start
+    // faster with fewer, larger CTAs; multi-wave calls balance better with 2-warp CTAs
+    wpb = (qm * d.batch <= 148LL * 36) ? 4 : default_warps;
+  }
   Launch l;
   l.block = dim3(32 * wpb);
   l.grid = dim3((unsigned)((qm + wpb - 1) / wpb), (unsigned)d.batch);
@@ -182,7 +186,11 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   cfg.stream = st;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
-  attr[0].val.programmaticStreamSerializationAllowed = g_no_pdl.load(std::memory_order_relaxed) ? 0 : 1;
+  // Only when the fill is short (grad_value fits in L2): behind a long fill the early-launched CTAs would just sit on
+  // the SMs the fill needs (C4DEC, 728 MB: 298 us with PDL vs 290 us without).
+  const size_t fill_bytes = sizeof(float) * (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  const bool pdl = !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20);
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const T* go_ = (const T*)go; const T* value_ = (const T*)value; const T* loc_ = (const T*)loc; const T* attn_ = (const T*)attn;

@@ -329,17 +329,18 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 // ------------------------------------------------------------------------------------------------
 // grad_value accumulates in fp32 (`gv`): the caller's tensor for T=float, a workspace for 16-bit T.
 //
-// Two passes, split by a programmatic-dependent-launch fence:
-//   pass 1  gathers the taps, forms per sample the four dot products <grad_out, tap> over the channels,
-//           reduces them across the LPR lanes, hands them back to the lane that owns the sample, which
-//           combines them into grad_attn / grad_loc and writes those coalesced.  Touches neither grad_value
-//           nor anything the preceding zero-fill kernel writes, so it runs CONCURRENTLY with that kernel
-//           (the fill triggers `griddepcontrol.launch_dependents` at its start);
-//   fence   `griddepcontrol.wait`: the zero-fill has completed and is visible;
-//   pass 2  recomputes the (cheap) geometry and scatters weight * attention * grad_out into grad_value with
-//           16-byte `red.global.add.v4.f32` (no return value, resolved in L2).
+// Per round a lane group gathers the 4 taps of its sample, forms the four dot products <grad_out, tap> over its
+// channels (FFMA2), reduces them across the LPR lanes and hands them back to the lane that owns the sample (which
+// combines them into grad_attn / grad_loc and writes those coalesced at the end); then it scatters
+// weight * attention * grad_out into grad_value with 16-byte `red.global.add.v4.f32` (fire-and-forget, resolved in
+// L2, so the scatter of one round overlaps the gathers of the next).
+//
+// Programmatic dependent launch: the kernel is released while the zero-fill of grad_value (previous kernel in the
+// stream, which triggers `griddepcontrol.launch_dependents` at its start) is still running; everything up to the first
+// scatter -- parameter loads, geometry, the first gather round -- overlaps the fill, and `griddepcontrol.wait`
+// orders the first `red` after its completion.
 template <typename T, int D, int MC, int U>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 10 : (U == 2 ? 9 : 6))
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 9 : (U == 2 ? 7 : 5))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
@@ -367,8 +368,8 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
 
   float go[VEC];
   Vec16<T>::unpack(ldg128(grad_out + u * D + cl * VEC), go);
+  bool fenced = false;
 
-  // ---------------- pass 1: grad_attn, grad_loc ----------------
   for (int base = 0; base < LP; base += 32) {
     SampleGeo sg;
     Geo<float> ge;
@@ -376,6 +377,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
     int H, W;
     const bool have = base + lane < LP;
     sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, MD, sg, ge, a, H, W);
+    const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
     float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;  // <grad_out, tap> of MY sample, from the group that gathered it
     for (int k0 = 0; k0 < cnt; k0 += G * U) {
@@ -386,7 +388,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         const int src = k0 + j * G + g;
         off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
         rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
-        if (src >= cnt) rsf[j] = 0;
+        if (src >= cnt) rsf[j] = 0;  // shfl wraps modulo 32: a lane group past the end must not gather / scatter
         full = full && ((rsf[j] & 15) == 15);
       }
       const bool all_ok = __all_sync(0xffffffffu, full);
@@ -423,6 +425,33 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         const float t11 = __shfl_sync(0xffffffffu, d[3], from);
         if (rel >= 0 && rel < G) { r00 = t00; r01 = t01; r10 = t10; r11 = t11; }
       }
+      // ---- scatter: needs the zero-fill of grad_value (previous kernel) complete and visible ----
+      if (!fenced) {
+        asm volatile("griddepcontrol.wait;" ::: "memory");
+        fenced = true;
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int src = k0 + j * G + g;
+        float w[4];
+        w[0] = __shfl_sync(0xffffffffu, w00, src);
+        w[1] = __shfl_sync(0xffffffffu, w01, src);
+        w[2] = __shfl_sync(0xffffffffu, w10, src);
+        w[3] = __shfl_sync(0xffffffffu, w11, src);
+        float* g0 = gb + off[j];
+        float* g1 = g0 + (rsf[j] >> 4);
+        float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
+#pragma unroll
+        for (int t = 0; t < 4; ++t)
+          if (rsf[j] & (1 << t)) {
+#pragma unroll
+            for (int i = 0; i < VEC; i += 4) {
+              const float2 lo = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i], go[i + 1]));
+              const float2 hi = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i + 2], go[i + 3]));
+              red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
+            }
+          }
+      }
     }
     if (have) {  // coalesced: 32 consecutive samples of the unit
       const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
@@ -432,44 +461,6 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
       const float gx = ge.hy * (r01 - r00) + ge.ly * (r11 - r10);
       const float gy = bot - top;
       store_xy(gloc + 2 * sidx, (float)W * a * gx, (float)H * a * gy);
-    }
-  }
-
-  // ---------------- fence: the zero-fill of grad_value (previous kernel in the stream) is complete ----------------
-  asm volatile("griddepcontrol.wait;" ::: "memory");
-
-  // ---------------- pass 2: scatter into grad_value ----------------
-  for (int base = 0; base < LP; base += 32) {
-    SampleGeo sg;
-    Geo<float> ge;
-    float a;
-    int H, W;
-    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, base + lane < LP, inv_p, MD, sg, ge, a, H, W);
-    const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
-    const int cnt = min(32, LP - base);
-    for (int k0 = 0; k0 < cnt; k0 += G) {
-      const int src = k0 + g;
-      const int off = __shfl_sync(0xffffffffu, sg.off00, src);
-      int rsf = __shfl_sync(0xffffffffu, sg.rsf, src);
-      float w[4];
-      w[0] = __shfl_sync(0xffffffffu, w00, src);
-      w[1] = __shfl_sync(0xffffffffu, w01, src);
-      w[2] = __shfl_sync(0xffffffffu, w10, src);
-      w[3] = __shfl_sync(0xffffffffu, w11, src);
-      if (src >= cnt) rsf = 0;
-      float* g0 = gb + off;
-      float* g1 = g0 + (rsf >> 4);
-      float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
-#pragma unroll
-      for (int t = 0; t < 4; ++t)
-        if (rsf & (1 << t)) {
-#pragma unroll
-          for (int i = 0; i < VEC; i += 4) {
-            const float2 lo = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i], go[i + 1]));
-            const float2 hi = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i + 2], go[i + 3]));
-            red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
-          }
-        }
     }
   }
 }
