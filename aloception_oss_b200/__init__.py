@@ -7,6 +7,10 @@ ops/modules/__init__.py:9):
 """
 from .functions import (  # noqa: F401
     MSDeformAttnFunction,
+    MSDeformAttnFusedFunction,
+    fused_supported,
+    ms_deform_attn_fused_backward,
+    ms_deform_attn_fused_forward,
     load_MultiScaleDeformableAttention,
     load_ops,
     ms_deform_attn_backward,
@@ -17,6 +21,7 @@ from .modules import MSDeformAttn  # noqa: F401
 
 __all__ = [
     "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "load_MultiScaleDeformableAttention", "load_ops",
-    "MSDeformAttn", "ms_deform_attn_forward", "ms_deform_attn_backward",
+    "MSDeformAttn", "ms_deform_attn_forward", "ms_deform_attn_backward", "MSDeformAttnFusedFunction",
+    "ms_deform_attn_fused_forward", "ms_deform_attn_fused_backward", "fused_supported",
 ]
 __version__ = "0.1.0"

@@ -86,6 +86,12 @@ def lib() -> ctypes.CDLL:
     L.msda_backward_workspace_bytes.argtypes = [dp, i]
     L.msda_backward.restype = i
     L.msda_backward.argtypes = [vp] * 10 + [sz, dp, i, i, vp]
+    L.msda_fused_supported.restype = i
+    L.msda_fused_supported.argtypes = [dp, i, i]
+    L.msda_fused_forward.restype = i
+    L.msda_fused_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, dp, i, vp]
+    L.msda_fused_backward.restype = i
+    L.msda_fused_backward.argtypes = [vp] * 5 + [i] + [vp] * 7 + [sz, dp, i, i, vp]
     L.msda_set_tuning.restype = i
     L.msda_set_tuning.argtypes = [ctypes.c_char_p, i]
     L.msda_get_tuning.restype = i

@@ -105,19 +105,19 @@ int pick_unroll(int knob, int fallback) {
 // ---------------------------------------------------------------------------------------------
 // forward dispatch
 // ---------------------------------------------------------------------------------------------
-template <typename T, int D, int MC>
+template <typename T, int D, int MC, bool FUSED = false>
 int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
-                   void* out, const msda_dims& d, cudaStream_t st) {
+                   void* out, const msda_dims& d, cudaStream_t st, const void* ref = nullptr, int ref_dim = 0) {
   const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
 #define MSDA_FWD(UU)                                                                                          \
-  msda::msda_fwd_sg_kernel<T, D, MC, UU><<<l.grid, l.block, 0, st>>>(                                         \
+  msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED><<<l.grid, l.block, 0, st>>>(                                  \
       (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
-      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads)
+      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim)
   if (U == 1) MSDA_FWD(1); else if (U == 2) MSDA_FWD(2); else MSDA_FWD(4);
 #undef MSDA_FWD
-  return check_launch("msda_forward(vector)");
+  return check_launch(FUSED ? "msda_fused_forward" : "msda_forward(vector)");
 }
 
 template <typename T>
@@ -171,9 +171,10 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   return check_launch("msda_backward(zero grad_value)");
 }
 
-template <typename T, int D, int MC>
+template <typename T, int D, int MC, bool FUSED = false>
 int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
-                   const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st) {
+                   const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st,
+                   const void* ref = nullptr, int ref_dim = 0, float* gref = nullptr) {
   const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
@@ -194,12 +195,12 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   cfg.attrs = attr;
   cfg.numAttrs = 1;
   const T* go_ = (const T*)go; const T* value_ = (const T*)value; const T* loc_ = (const T*)loc; const T* attn_ = (const T*)attn;
-  T* gloc_ = (T*)gloc; T* gattn_ = (T*)gattn;
+  T* gloc_ = (T*)gloc; T* gattn_ = (T*)gattn; const T* ref_ = (const T*)ref;
   const int S = d.spatial_size, M = d.num_heads, L = d.num_levels, P = d.num_point, QM = d.num_query * d.num_heads;
   cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
-  e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU>, go_, value_, shapes, start, loc_, attn_, gv, \
-                         gloc_, gattn_, S, M, L, P, inv_p, QM)
+  e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED>, go_, value_, shapes, start, loc_, attn_, \
+                         gv, gloc_, gattn_, S, M, L, P, inv_p, QM, ref_, ref_dim, gref)
   if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4);
 #undef MSDA_BWD
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -258,6 +259,78 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
       if (blocks > 148 * 16) blocks = 148 * 16;
       msda::msda_cvt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)acc, (T*)grad_value, (long long)n_value);
       if (int rc = check_launch("msda_backward(convert grad_value)")) return rc;
+    }
+  }
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------------
+// fused operator (softmax + location arithmetic in the kernel); vector kernels only -> rc 2 = "unsupported here"
+// ---------------------------------------------------------------------------------------------
+constexpr int kUnsupported = 2;
+
+bool fused_shape_ok(const msda_dims& d, int dtype, int ref_dim) {
+  return vec_shape_ok(d) && dtype != MSDA_F64 && (ref_dim == 2 || ref_dim == 4) && d.num_levels * d.num_point >= 1 &&
+         d.num_levels * d.num_point <= 32 &&
+         (d.channels == 16 || d.channels == 32 || d.channels == 64 || d.channels == 128);
+}
+
+template <typename T>
+int fused_forward_typed(const void* value, const int32_t* shapes, const int32_t* start, const void* ref, int ref_dim,
+                        const void* off, const void* logits, void* out, const msda_dims& d, cudaStream_t st) {
+  if (!(aligned(value, 16) && aligned(out, 16) && aligned(off, 2 * sizeof(T)) && aligned(logits, sizeof(T)) &&
+        aligned(ref, sizeof(T))))
+    return kUnsupported;
+#define MSDA_CASE(DD)                                                                                         \
+  case DD:                                                                                                    \
+    return d.num_heads == 8                                                                                   \
+               ? launch_fwd_vec<T, DD, 8, true>(value, shapes, start, off, logits, out, d, st, ref, ref_dim)   \
+               : launch_fwd_vec<T, DD, 0, true>(value, shapes, start, off, logits, out, d, st, ref, ref_dim);
+  switch (d.channels) {
+    MSDA_CASE(16)
+    MSDA_CASE(32)
+    MSDA_CASE(64)
+    MSDA_CASE(128)
+    default: break;
+  }
+#undef MSDA_CASE
+  return kUnsupported;
+}
+
+template <typename T>
+int fused_backward_typed(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* ref,
+                         int ref_dim, const void* off, const void* logits, void* grad_value, void* goff, void* glogits,
+                         float* gref, void* workspace, const msda_dims& d, cudaStream_t st) {
+  constexpr bool needs_ws = sizeof(T) != sizeof(float);
+  const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  float* acc = needs_ws ? (float*)workspace : (float*)grad_value;
+  if (!(aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) && aligned(off, 2 * sizeof(T)) &&
+        aligned(goff, 2 * sizeof(T)) && aligned(logits, sizeof(T)) && aligned(ref, sizeof(T))))
+    return kUnsupported;
+  if (int rc = zero_fill(acc, n_value * sizeof(float), st)) return rc;
+  int rc = kUnsupported;
+#define MSDA_CASE(DD)                                                                                                  \
+  case DD:                                                                                                             \
+    rc = d.num_heads == 8 ? launch_bwd_vec<T, DD, 8, true>(go, value, shapes, start, off, logits, acc, goff, glogits, d, \
+                                                           st, ref, ref_dim, gref)                                      \
+                          : launch_bwd_vec<T, DD, 0, true>(go, value, shapes, start, off, logits, acc, goff, glogits, d, \
+                                                           st, ref, ref_dim, gref);                                     \
+    break;
+  switch (d.channels) {
+    MSDA_CASE(16)
+    MSDA_CASE(32)
+    MSDA_CASE(64)
+    MSDA_CASE(128)
+    default: break;
+  }
+#undef MSDA_CASE
+  if (rc != 0) return rc;
+  if constexpr (needs_ws) {
+    if (n_value > 0) {
+      long long blocks = (long long)((n_value + 256 * 8 - 1) / (256 * 8));
+      if (blocks > 148 * 16) blocks = 148 * 16;
+      msda::msda_cvt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const float*)acc, (T*)grad_value, (long long)n_value);
+      if (int rc2 = check_launch("msda_fused_backward(convert grad_value)")) return rc2;
     }
   }
   return 0;
@@ -402,6 +475,73 @@ int msda_forward_host(const void* value, const int32_t* spatial_shapes, const in
   cudaFreeAsync(dev, st);
   const cudaError_t se = cudaStreamSynchronize(st);
   if (rc == 0 && se != cudaSuccess) rc = fail("stream synchronize: %s", cudaGetErrorString(se));
+  return rc;
+}
+
+int msda_fused_supported(const msda_dims* dims, int dtype, int ref_dim) {
+  if (!dims || elt_size(dtype) == 0) return 0;
+  return fused_shape_ok(*dims, dtype, ref_dim) ? 1 : 0;
+}
+
+int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                       const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                       void* output, const msda_dims* dims, int dtype, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate_dims(dims, dtype)) return rc;
+  const msda_dims& d = *dims;
+  if (!fused_shape_ok(d, dtype, ref_dim)) {
+    fail("msda_fused_forward: shape/dtype outside the fused kernels (need L*P <= 32, D in {16,32,64,128}, no f64)");
+    return kUnsupported;
+  }
+  const long long units = (long long)d.batch * d.num_query * d.num_heads;
+  if (units == 0) return 0;
+  if (!value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets || !attn_logits || !output)
+    return fail("NULL tensor pointer passed to msda_fused_forward");
+  cudaStream_t st = (cudaStream_t)stream;
+  int rc = kUnsupported;
+  switch (dtype) {
+    case MSDA_F32: rc = fused_forward_typed<float>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
+    case MSDA_BF16: rc = fused_forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
+    case MSDA_F16: rc = fused_forward_typed<__half>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
+    default: break;
+  }
+  if (rc == kUnsupported) fail("msda_fused_forward: misaligned tensors");
+  return rc;
+}
+
+int msda_fused_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
+                        const int32_t* level_start_index, const void* reference_points, int ref_dim,
+                        const void* sampling_offsets, const void* attn_logits, void* grad_value, void* grad_offsets,
+                        void* grad_logits, float* grad_reference_points, void* workspace, size_t workspace_bytes,
+                        const msda_dims* dims, int dtype, int flags, void* stream) {
+  g_err[0] = 0;
+  if (int rc = validate_dims(dims, dtype)) return rc;
+  if (flags != 0) return fail("flags must be 0");
+  const msda_dims& d = *dims;
+  if (!fused_shape_ok(d, dtype, ref_dim)) {
+    fail("msda_fused_backward: shape/dtype outside the fused kernels");
+    return kUnsupported;
+  }
+  const long long units = (long long)d.batch * d.num_query * d.num_heads;
+  const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  const size_t need = msda_backward_workspace_bytes(dims, dtype);
+  if (need > 0 && n_value > 0 && (!workspace || workspace_bytes < need))
+    return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
+  if (n_value > 0 && !grad_value) return fail("grad_value is NULL");
+  cudaStream_t st = (cudaStream_t)stream;
+  if (units == 0) return zero_fill(need ? workspace : grad_value, n_value * sizeof(float), st) ||
+                         (need ? zero_fill(grad_value, n_value * elt_size(dtype), st) : 0);
+  if (!grad_output || !value || !spatial_shapes || !level_start_index || !reference_points || !sampling_offsets ||
+      !attn_logits || !grad_offsets || !grad_logits)
+    return fail("NULL tensor pointer passed to msda_fused_backward");
+  int rc = kUnsupported;
+  switch (dtype) {
+    case MSDA_F32: rc = fused_backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
+    case MSDA_BF16: rc = fused_backward_typed<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
+    case MSDA_F16: rc = fused_backward_typed<__half>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
+    default: break;
+  }
+  if (rc == kUnsupported) fail("msda_fused_backward: misaligned tensors");
   return rc;
 }
 

@@ -199,22 +199,82 @@ struct SampleGeo {
   int rsf;    // (W * M * D) << 4 | ok11 << 3 | ok10 << 2 | ok01 << 1 | ok00
 };
 
+// What one sample needs before its geometry: location, attention weight, level shape.
+struct SampleParams {
+  float lx, ly, a;  // normalised location (x, y), attention weight
+  int H, W, st;     // level shape and first row
+};
+
+// plain operator: locations and (already normalised) weights are inputs
 template <typename T>
-__device__ __forceinline__ void sample_geometry(const T* __restrict__ u_loc, const T* __restrict__ u_att,
-                                                const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
-                                                int s, bool have, float inv_p, int MD, SampleGeo& sg, Geo<float>& ge,
-                                                float& a, int& H, int& W) {
+__device__ __forceinline__ SampleParams load_params(const T* __restrict__ u_loc, const T* __restrict__ u_att,
+                                                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                                                    int s, bool have, float inv_p) {
+  SampleParams p;
   const int si = have ? s : 0;
   const int l = have ? level_of(si, inv_p) : 0;
-  float lx, ly;
-  load_xy(u_loc + 2 * si, lx, ly);
-  a = load_s(u_att + si);
-  H = __ldg(shapes + 2 * l);
-  W = __ldg(shapes + 2 * l + 1);
-  const int st = __ldg(start + l);
-  ge = make_geo<float>(lx, ly, H, W, have);
-  sg.off00 = (st + ge.row00) * MD;
-  sg.rsf = ((W * MD) << 4) | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
+  load_xy(u_loc + 2 * si, p.lx, p.ly);
+  p.a = load_s(u_att + si);
+  p.H = __ldg(shapes + 2 * l);
+  p.W = __ldg(shapes + 2 * l + 1);
+  p.st = __ldg(start + l);
+  return p;
+}
+
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+  return v;
+}
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// Fused operator (the elementwise part of MSDeformAttn.forward, reference ops/modules/ms_deform_attn.py:121-137, done in
+// the kernel): inputs are the RAW sampling offsets and attention logits of the two Linear layers plus the reference
+// points; lane i produces  A_i = softmax_i(logits over the unit's L*P samples)  and
+//   2-d refs:  loc = ref_xy + off / (W_l, H_l)            4-d refs:  loc = ref_xy + off / P * ref_wh * 0.5
+// with the same operation order / roundings as the eager PyTorch expression.  Needs L*P <= 32 (one lane per sample).
+// `od` returns off / P (4-d) for the reference-point gradient.
+template <typename T>
+__device__ __forceinline__ SampleParams fused_params(const T* __restrict__ u_off, const T* __restrict__ u_logit,
+                                                     const T* __restrict__ ref_q, int RD,
+                                                     const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                                                     int s, bool have, float inv_p, int P, int& l, float& odx, float& ody) {
+  SampleParams p;
+  const int si = have ? s : 0;
+  l = have ? level_of(si, inv_p) : 0;
+  float ox, oy;
+  load_xy(u_off + 2 * si, ox, oy);
+  const float logit = have ? load_s(u_logit + si) : -INFINITY;
+  p.H = __ldg(shapes + 2 * l);
+  p.W = __ldg(shapes + 2 * l + 1);
+  p.st = __ldg(start + l);
+  const float rx = load_s(ref_q + l * RD), ry = load_s(ref_q + l * RD + 1);
+  if (RD == 2) {
+    odx = 0.f; ody = 0.f;
+    p.lx = __fadd_rn(rx, __fdiv_rn(ox, (float)p.W));
+    p.ly = __fadd_rn(ry, __fdiv_rn(oy, (float)p.H));
+  } else {
+    const float rw = load_s(ref_q + l * RD + 2), rh = load_s(ref_q + l * RD + 3);
+    odx = __fdiv_rn(ox, (float)P);
+    ody = __fdiv_rn(oy, (float)P);
+    p.lx = __fadd_rn(rx, __fmul_rn(__fmul_rn(odx, rw), 0.5f));
+    p.ly = __fadd_rn(ry, __fmul_rn(__fmul_rn(ody, rh), 0.5f));
+  }
+  const float mx = warp_max(logit);
+  const float e = have ? expf(logit - mx) : 0.f;
+  const float sum = warp_sum(e);
+  p.a = __fdiv_rn(e, sum);
+  return p;
+}
+
+__device__ __forceinline__ void finish_geometry(const SampleParams& p, bool have, int MD, SampleGeo& sg, Geo<float>& ge) {
+  ge = make_geo<float>(p.lx, p.ly, p.H, p.W, have);
+  sg.off00 = (p.st + ge.row00) * MD;
+  sg.rsf = ((p.W * MD) << 4) | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
 }
 
 // the four tap pointers of one sample; `all_ok` is warp-uniform
@@ -242,12 +302,13 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
 // Register budgets via min-CTAs/SM at 128 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 56 regs (36 warps/SM, keeps the
 // 4 800-unit C2 call in ONE wave), U=4 -> 80 regs (24 warps/SM).
-template <typename T, int D, int MC, int U>
+// FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits, `ref` the reference points (last dim RD).
+template <typename T, int D, int MC, int U, bool FUSED>
 __global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 12 : (U == 2 ? 9 : 6))
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int Mrt, int L, int P, float inv_p, int QM) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
@@ -270,12 +331,20 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 #pragma unroll
   for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 
-  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane
+  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
     SampleGeo sg;
     Geo<float> ge;
-    float a;
-    int H, W;
-    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, base + lane < LP, inv_p, MD, sg, ge, a, H, W);
+    SampleParams sp;
+    const bool have = base + lane < LP;
+    if constexpr (FUSED) {
+      int l;
+      float odx, ody;
+      sp = fused_params<T>(u_loc, u_att, ref + ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
+    } else {
+      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+    }
+    finish_geometry(sp, have, MD, sg, ge);
+    const float a = sp.a;
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
     for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
@@ -339,13 +408,17 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 // stream, which triggers `griddepcontrol.launch_dependents` at its start) is still running; everything up to the first
 // scatter -- parameter loads, geometry, the first gather round -- overlaps the fill, and `griddepcontrol.wait`
 // orders the first `red` after its completion.
-template <typename T, int D, int MC, int U>
+// FUSED: `loc` / `attn` are the raw offsets / logits, `gloc` / `gattn` receive the gradients w.r.t. THOSE (softmax and
+// location arithmetic differentiated in the kernel), `gref` (fp32, pre-zeroed, may be null) accumulates the gradient
+// w.r.t. the reference points with scalar reds (M*P contributions per element).
+template <typename T, int D, int MC, int U, bool FUSED>
 __global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 9 : (U == 2 ? 7 : 5))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
                    T* __restrict__ gloc, T* __restrict__ gattn,
-                   int S, int Mrt, int L, int P, float inv_p, int QM) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
+                   float* __restrict__ gref) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
@@ -373,10 +446,18 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   for (int base = 0; base < LP; base += 32) {
     SampleGeo sg;
     Geo<float> ge;
-    float a;
-    int H, W;
+    SampleParams sp;
+    int lvl = 0;
+    float odx = 0.f, ody = 0.f;
     const bool have = base + lane < LP;
-    sample_geometry<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, MD, sg, ge, a, H, W);
+    if constexpr (FUSED) {
+      sp = fused_params<T>(u_loc, u_att, ref + ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, lvl, odx, ody);
+    } else {
+      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+    }
+    finish_geometry(sp, have, MD, sg, ge);
+    const float a = sp.a;
+    const int H = sp.H, W = sp.W;
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
     float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;  // <grad_out, tap> of MY sample, from the group that gathered it
@@ -453,14 +534,40 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
           }
       }
     }
-    if (have) {  // coalesced: 32 consecutive samples of the unit
-      const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
-      const float bot = ge.hx * r10 + ge.lx * r11;  // ... on row y0 + 1
-      const long long sidx = u * LP + base + lane;
-      gattn[sidx] = from_acc<T>(ge.hy * top + ge.ly * bot);
-      const float gx = ge.hy * (r01 - r00) + ge.ly * (r11 - r10);
-      const float gy = bot - top;
-      store_xy(gloc + 2 * sidx, (float)W * a * gx, (float)H * a * gy);
+    const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
+    const float bot = ge.hx * r10 + ge.lx * r11;  // ... on row y0 + 1
+    const float g_a = ge.hy * top + ge.ly * bot;                                  // d out / d A_i
+    const float g_lx = (float)W * a * (ge.hy * (r01 - r00) + ge.ly * (r11 - r10));  // d out / d loc_x
+    const float g_ly = (float)H * a * (bot - top);                                  // d out / d loc_y
+    const long long sidx = u * LP + base + lane;
+    if constexpr (!FUSED) {
+      if (have) {  // coalesced: 32 consecutive samples of the unit
+        gattn[sidx] = from_acc<T>(g_a);
+        store_xy(gloc + 2 * sidx, g_lx, g_ly);
+      }
+    } else {
+      // softmax backward over the unit's samples:  g_logit_i = A_i * (g_A_i - sum_j A_j g_A_j)
+      const float dot = warp_sum(have ? a * g_a : 0.f);
+      if (have) {
+        gattn[sidx] = from_acc<T>(a * (g_a - dot));
+        const long long rbase = (((long long)blockIdx.y * (QM / M) + uq / M) * L + lvl) * RD;
+        if (RD == 2) {
+          store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx, (float)W), __fdiv_rn(g_ly, (float)H));
+          if (gref != nullptr) {
+            atomicAdd(gref + rbase, g_lx);
+            atomicAdd(gref + rbase + 1, g_ly);
+          }
+        } else {
+          const float rw = load_s(ref + rbase + 2), rh = load_s(ref + rbase + 3);
+          store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx * 0.5f * rw, (float)P), __fdiv_rn(g_ly * 0.5f * rh, (float)P));
+          if (gref != nullptr) {
+            atomicAdd(gref + rbase, g_lx);
+            atomicAdd(gref + rbase + 1, g_ly);
+            atomicAdd(gref + rbase + 2, g_lx * 0.5f * odx);
+            atomicAdd(gref + rbase + 3, g_ly * 0.5f * ody);
+          }
+        }
+      }
     }
   }
 }

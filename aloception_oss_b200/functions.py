@@ -145,6 +145,108 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     return [grad_value, grad_loc, grad_attn]
 
 
+# ------------------------------------------------------------------------------------------------------------
+# fused operator: softmax + sampling-location arithmetic of MSDeformAttn.forward inside the kernels
+# (reference ops/modules/ms_deform_attn.py:121-137 + the op)
+# ------------------------------------------------------------------------------------------------------------
+def _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits):
+    if sampling_offsets.dim() != 6 or sampling_offsets.shape[-1] != 2:
+        raise RuntimeError(f"sampling_offsets must be (N, Lq, M, L, P, 2), got {tuple(sampling_offsets.shape)}")
+    N, S, M, D = value.shape
+    _, Lq, M2, L, P, _ = sampling_offsets.shape
+    if M2 != M or spatial_shapes.shape[0] != L:
+        raise RuntimeError("sampling_offsets inconsistent with value / spatial_shapes")
+    if attn_logits.numel() != N * Lq * M * L * P:
+        raise RuntimeError(f"attn_logits must hold N*Lq*M*L*P = {N * Lq * M * L * P} elements")
+    if reference_points.dim() != 4 or tuple(reference_points.shape[:3]) != (N, Lq, L) or reference_points.shape[-1] not in (2, 4):
+        raise ValueError(
+            "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+    return _capi.MsdaDims(N, S, M, D, L, Lq, P), int(reference_points.shape[-1])
+
+
+def fused_supported(value, spatial_shapes, reference_points, sampling_offsets, attn_logits) -> bool:
+    """True when the fused kernels serve this problem (else compose softmax / location arithmetic + the plain op)."""
+    if not value.is_cuda or value.dtype not in (torch.float32, torch.bfloat16, torch.float16):
+        return False
+    dims, rd = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
+    return bool(_capi.lib().msda_fused_supported(ctypes.byref(dims), _DTYPES[value.dtype], rd))
+
+
+def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                 attn_logits):
+    """(N,S,M,D), (L,2), (L,), (N,Lq,L,2|4), raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P) -> (N, Lq, M*D)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits)]
+    _check_inputs(named)
+    for name, t in named[3:]:
+        if t.dtype != value.dtype or t.device != value.device:
+            raise RuntimeError(f"{name} must have value's dtype and device")
+    dims, rd = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
+    shapes = _meta_i32(spatial_shapes, "spatial_shapes")
+    start = _meta_i32(level_start_index, "level_start_index")
+    out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=value.device)
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = _capi.lib().msda_fused_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
+                                            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(out), ctypes.byref(dims),
+                                            _DTYPES[value.dtype], ctypes.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError("msda_fused_forward failed: " + _capi.last_error())
+    return out
+
+
+def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                  attn_logits, grad_output, need_grad_ref=True):
+    """-> (grad_value, grad_reference_points | None, grad_sampling_offsets, grad_attn_logits)."""
+    named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
+             ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
+             ("grad_output", grad_output)]
+    _check_inputs(named)
+    dims, rd = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
+    shapes = _meta_i32(spatial_shapes, "spatial_shapes")
+    start = _meta_i32(level_start_index, "level_start_index")
+    grad_value = torch.empty_like(value)
+    grad_off = torch.empty_like(sampling_offsets)
+    grad_logits = torch.empty_like(attn_logits)
+    grad_ref = torch.zeros(reference_points.shape, dtype=torch.float32, device=value.device) if need_grad_ref else None
+    L = _capi.lib()
+    dt = _DTYPES[value.dtype]
+    ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    with torch.cuda.device(value.device):
+        stream = torch.cuda.current_stream().cuda_stream
+        rc = L.msda_fused_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
+                                   _ptr(sampling_offsets), _ptr(attn_logits), _ptr(grad_value), _ptr(grad_off),
+                                   _ptr(grad_logits), _ptr(grad_ref) if grad_ref is not None else ctypes.c_void_p(0),
+                                   _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, ctypes.byref(dims), dt, 0,
+                                   ctypes.c_void_p(stream))
+    if rc != 0:
+        raise RuntimeError("msda_fused_backward failed: " + _capi.last_error())
+    if grad_ref is not None and grad_ref.dtype != value.dtype:
+        grad_ref = grad_ref.to(value.dtype)
+    return grad_value, grad_ref, grad_off, grad_logits
+
+
+class MSDeformAttnFusedFunction(Function):
+    """``apply(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits)``
+    == softmax + location arithmetic + ``MSDeformAttnFunction`` of the reference module, in one kernel per pass."""
+
+    @staticmethod
+    def forward(ctx, value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits):
+        out = ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
+                                           attn_logits)
+        ctx.save_for_backward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets, attn_logits)
+        return out
+
+    @staticmethod
+    @once_differentiable
+    def backward(ctx, grad_output):
+        value, shapes, start, ref, off, logits = ctx.saved_tensors
+        gv, gref, goff, glog = ms_deform_attn_fused_backward(value, shapes, start, ref, off, logits,
+                                                             grad_output.contiguous(), need_grad_ref=ctx.needs_input_grad[3])
+        return gv, None, None, gref, goff, glog
+
+
 def load_ops():
     """Reference: torch.ops.load_library(<build dir>/MultiScaleDeformableAttention.so).  Here: load the C-ABI
     library and make sure ``torch.ops.alonet_custom.ms_deform_attn_{forward,backward}`` exist."""

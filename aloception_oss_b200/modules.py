@@ -15,7 +15,8 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from .functions import MSDeformAttnFunction, load_MultiScaleDeformableAttention, ms_deform_attn_core_pytorch
+from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported,
+                        load_MultiScaleDeformableAttention, ms_deform_attn_core_pytorch)
 
 
 def _is_power_of_2(n):
@@ -25,8 +26,13 @@ def _is_power_of_2(n):
 
 
 class MSDeformAttn(nn.Module):
-    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4):
+    def __init__(self, d_model=256, n_levels=4, n_heads=8, n_points=4, fused=True):
+        """Same arguments as the reference.  ``fused`` (extension, default on): softmax and the sampling-location
+        arithmetic run inside the sampling kernels instead of ~5 elementwise kernels (same maths, same roundings of
+        the locations).  ``fused=False`` reproduces the reference's op sequence."""
         super().__init__()
+        self.fused = fused
+        self._validated_levels = set()
         if d_model % n_heads != 0:
             raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
         if not _is_power_of_2(d_model // n_heads):
@@ -44,6 +50,20 @@ class MSDeformAttn(nn.Module):
         self.output_proj = nn.Linear(d_model, d_model)
         self._reset_parameters()
         load_MultiScaleDeformableAttention()
+
+    def _check_level_sizes(self, input_spatial_shapes, Len_in):
+        """The reference asserts ``sum_l H_l*W_l == Len_in`` on every call (ms_deform_attn.py:113), which costs a
+        device->host sync per layer when the shapes live on the GPU.  Same check here, but remembered per shapes tensor
+        (storage pointer + version counter) and skipped while a CUDA graph is being captured (a sync is illegal there)."""
+        key = (input_spatial_shapes.data_ptr(), input_spatial_shapes._version, int(Len_in))
+        if key in self._validated_levels:
+            return
+        if input_spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
+            return
+        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
+        if len(self._validated_levels) > 64:
+            self._validated_levels.clear()
+        self._validated_levels.add(key)
 
     def _reset_parameters(self):
         # compass-pattern offset bias, zero attention logits, xavier projections (ms_deform_attn.py:70-88)
@@ -69,7 +89,7 @@ class MSDeformAttn(nn.Module):
         -> (N, Lq, C)."""
         N, Len_q, _ = query.shape
         N, Len_in, _ = input_flatten.shape
-        assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
+        self._check_level_sizes(input_spatial_shapes, Len_in)
 
         value = self.value_proj(input_flatten)
         if input_padding_mask is not None:
@@ -77,6 +97,15 @@ class MSDeformAttn(nn.Module):
         value = value.view(N, Len_in, self.n_heads, self.d_model // self.n_heads)
         offsets = self.sampling_offsets(query).view(N, Len_q, self.n_heads, self.n_levels, self.n_points, 2)
         weights = self.attention_weights(query).view(N, Len_q, self.n_heads, self.n_levels * self.n_points)
+        if reference_points.shape[-1] not in (2, 4):
+            raise ValueError(
+                "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+        if self.fused and "is_tracing" not in kwargs and fused_supported(value, input_spatial_shapes, reference_points,
+                                                                        offsets, weights):
+            output = MSDeformAttnFusedFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
+                                                     reference_points.contiguous(), offsets.contiguous(),
+                                                     weights.contiguous())
+            return self.output_proj(output)
         weights = F.softmax(weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:
             normalizer = torch.stack([input_spatial_shapes[..., 1], input_spatial_shapes[..., 0]], -1)

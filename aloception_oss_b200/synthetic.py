@@ -181,3 +181,58 @@ def device_inputs(w: Workload, seed: int, device, dtype=None, loc_mode: str = "u
         attn=attn.to(dtype).contiguous(),
         grad_out=grad_out.to(dtype).contiguous(),
     )
+
+
+# ------------------------------------------------------------------------------------------------------------
+# module-level cases (MSDeformAttn.forward incl. projections) -- shared by oracle/make_golden_module.py and the tests
+# ------------------------------------------------------------------------------------------------------------
+MODULE_CASES = {
+    # name: (d_model, n_levels, n_heads, n_points, levels, N, Lq, ref_dim, with_mask)
+    "mod_ref2_d256": (256, 4, 8, 4, ((12, 16), (6, 8), (3, 4), (2, 2)), 2, 37, 2, True),
+    "mod_ref4_d128": (128, 3, 4, 2, ((9, 5), (4, 3), (2, 1)), 2, 19, 4, False),
+}
+
+
+def module_case(name: str, seed: int = 11):
+    """Deterministic weights + inputs of one MSDeformAttn module case, as numpy float32 arrays.
+
+    Returns (cfg dict, state dict, inputs dict).  Weights are drawn here (not taken from ``_reset_parameters``) so that
+    offsets and attention logits depend on the query and every parameter receives a non-trivial gradient."""
+    d_model, L, M, P, levels, N, Lq, ref_dim, with_mask = MODULE_CASES[name]
+    rng = np.random.default_rng(seed)
+    S = int(sum(h * w for h, w in levels))
+
+    def nrm(shape, scale):
+        return (rng.standard_normal(shape) * scale).astype(np.float32)
+
+    state = {
+        "sampling_offsets.weight": nrm((M * L * P * 2, d_model), 0.03),
+        "sampling_offsets.bias": nrm((M * L * P * 2,), 1.5),
+        "attention_weights.weight": nrm((M * L * P, d_model), 0.1),
+        "attention_weights.bias": nrm((M * L * P,), 0.1),
+        "value_proj.weight": nrm((d_model, d_model), 0.06),
+        "value_proj.bias": nrm((d_model,), 0.01),
+        "output_proj.weight": nrm((d_model, d_model), 0.06),
+        "output_proj.bias": nrm((d_model,), 0.01),
+    }
+    shapes, start = level_tensors(levels)
+    ref_xy = rng.random((N, Lq, L, 2), dtype=np.float32)
+    if ref_dim == 4:
+        ref = np.concatenate([ref_xy, rng.random((N, Lq, L, 2), dtype=np.float32) * np.float32(0.4)], -1)
+    else:
+        ref = ref_xy
+    mask = np.zeros((N, S), dtype=bool)
+    if with_mask:
+        mask[:, -5:] = True
+        mask[1, 3:9] = True
+    inputs = {
+        "query": nrm((N, Lq, d_model), 1.0),
+        "reference_points": ref,
+        "input_flatten": nrm((N, S, d_model), 1.0),
+        "shapes": shapes,
+        "start": start,
+        "mask": mask if with_mask else None,
+        "grad_out": nrm((N, Lq, d_model), 1.0),
+    }
+    cfg = dict(d_model=d_model, n_levels=L, n_heads=M, n_points=P, levels=levels, N=N, Lq=Lq, ref_dim=ref_dim, S=S)
+    return cfg, state, inputs

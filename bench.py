@@ -276,14 +276,20 @@ def main():
     ms_bwd = time_graph(g_b, reps) / K_eff
     peak, peak_src = hbm_peak()
 
-    def roof(bytes_, ms, what):
+    try:
+        with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
+            traffic = json.load(f).get(f"{w.name}/{args.dtype}", {})
+    except Exception:
+        traffic = {}
+
+    def roof(bytes_, ms, what, tkey=None):
         ach = bytes_ / (ms * 1e-3) / 1e9
         return {"bound": "hbm", "kernel": what, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": None, "algorithmic_bytes": bytes_, "us_per_launch": round(ms * 1e3, 3),
+                "frac": round(ach / peak, 4), "traffic": traffic.get(tkey), "algorithmic_bytes": bytes_, "us_per_launch": round(ms * 1e3, 3),
                 "peak_source": peak_src}
 
-    r_fwd = roof(w.algorithmic_bytes(elt, False), ms_fwd, "msda_fwd_vec_kernel (forward pass)")
-    r_bwd = roof(w.algorithmic_bytes(elt, True), ms_bwd, "msda_zero_kernel + msda_bwd_vec_kernel (backward pass)")
+    r_fwd = roof(w.algorithmic_bytes(elt, False), ms_fwd, "msda_fwd_sg_kernel (forward pass)", "fwd")
+    r_bwd = roof(w.algorithmic_bytes(elt, True), ms_bwd, "msda_zero_kernel + msda_bwd_sg_kernel (backward pass, PDL-overlapped)", "bwd")
     dominant = r_bwd if ms_bwd >= ms_fwd else r_fwd
 
     # ---- eager (no graph) rate: what a Python caller gets launch-by-launch ------------------------------------

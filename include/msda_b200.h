@@ -101,6 +101,30 @@ int msda_forward_host(const void* value, const int32_t* spatial_shapes, const in
                       int dtype, void* stream);
 
 /*
+ * Fused operator: the elementwise part of `MSDeformAttn.forward` done inside the kernels
+ * (alonet/deformable_detr/ops/modules/ms_deform_attn.py:121-137 -- softmax of the attention logits over L*P, and
+ * sampling_locations = reference_points + offsets / (W_l, H_l)            for reference_points (N, Lq, L, 2), or
+ *                     = ref_xy + offsets / P * ref_wh * 0.5               for reference_points (N, Lq, L, 4)),
+ * followed by the same sampling as msda_forward.  Inputs are the RAW outputs of the two Linear layers:
+ *   sampling_offsets (N, Lq, M, L, P, 2), attn_logits (N, Lq, M, L*P); reference_points (N, Lq, L, ref_dim).
+ * This is SURVEY.md section 8(f) row 1 (the reference materialises sampling_locations / attention_weights with ~5
+ * elementwise kernels per call).  Served by the vector kernels only: msda_fused_supported() tells whether a
+ * problem qualifies (L*P <= 32, D in {16,32,64,128}, f32/bf16/f16); otherwise the entry points return 2 and the
+ * caller composes the unfused operator.
+ * msda_fused_backward: grad_offsets / grad_logits are gradients w.r.t. the raw inputs; grad_reference_points
+ * (fp32, (N, Lq, L, ref_dim), ZEROED BY THE CALLER, may be NULL) is accumulated with reds.
+ */
+int msda_fused_supported(const msda_dims* dims, int dtype, int ref_dim);
+int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                       const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                       void* output, const msda_dims* dims, int dtype, void* stream);
+int msda_fused_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
+                        const int32_t* level_start_index, const void* reference_points, int ref_dim,
+                        const void* sampling_offsets, const void* attn_logits, void* grad_value, void* grad_offsets,
+                        void* grad_logits, float* grad_reference_points, void* workspace, size_t workspace_bytes,
+                        const msda_dims* dims, int dtype, int flags, void* stream);
+
+/*
  * Tuning knobs (benchmark / test use).  Unknown names return non-zero.  Names:
  *   "force_generic"    0|1   route every call through the shape-generic kernels
  *   "fwd_unroll"       0=auto, 1, 2 or 4 samples in flight per lane group in the vector forward kernel

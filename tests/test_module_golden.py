@@ -1,0 +1,112 @@
+"""MSDeformAttn module against golden vectors of the reference MODULE (tests/golden_module/, produced by
+oracle/make_golden_module.py from the unmodified reference class).
+
+CPU: our module mirror on its tracing (pure-PyTorch) branch in float64 -- pins the mirror and the fixtures.
+GPU: the same module through the CUDA operator, unfused (reference op sequence) and FUSED (softmax + location arithmetic
+in the kernels), in float32.
+"""
+import os
+
+import numpy as np
+import pytest
+import torch
+
+import aloception_oss_b200 as msda
+from aloception_oss_b200.synthetic import MODULE_CASES, module_case
+from tests._util import assert_close, rms
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden_module")
+
+
+def run_module(name, device, dtype, fused, tracing):
+    cfg, state, x = module_case(name)
+    mod = msda.MSDeformAttn(cfg["d_model"], cfg["n_levels"], cfg["n_heads"], cfg["n_points"], fused=fused)
+    mod.load_state_dict({k: torch.from_numpy(v) for k, v in state.items()})
+    mod = mod.to(device=device, dtype=dtype)
+    t = lambda a: torch.from_numpy(a).to(device=device, dtype=dtype)
+    q, ref, src = t(x["query"]).requires_grad_(True), t(x["reference_points"]).requires_grad_(True), t(x["input_flatten"]).requires_grad_(True)
+    mask = None if x["mask"] is None else torch.from_numpy(x["mask"]).to(device)
+    shapes, start = torch.from_numpy(x["shapes"]).to(device), torch.from_numpy(x["start"]).to(device)
+    kw = {"is_tracing": None} if tracing else {}
+    out = mod(q, ref, src, shapes, start, mask, **kw)
+    out.backward(t(x["grad_out"]))
+    res = {"out": out, "g_query": q.grad, "g_ref": ref.grad, "g_src": src.grad}
+    for k, p in mod.named_parameters():
+        res["gp_" + k] = p.grad
+    return {k: v.detach().double().cpu().numpy() for k, v in res.items()}
+
+
+def compare(got, name, rtol):
+    ref = np.load(os.path.join(GOLD, name + ".npz"))
+    for k in ref.files:
+        if k == "name":
+            continue
+        want = ref[k].astype(np.float64)
+        assert_close(got[k], want, rtol, rtol * rms(want), f"{name}:{k}")
+
+
+def test_fixtures_present():
+    assert sorted(os.path.splitext(f)[0] for f in os.listdir(GOLD)) == sorted(MODULE_CASES)
+
+
+@pytest.mark.parametrize("name", sorted(MODULE_CASES))
+def test_module_mirror_tracing_branch_matches_reference_module(name):
+    compare(run_module(name, "cpu", torch.float64, fused=False, tracing=True), name, 2e-6)  # fixtures are stored in fp32
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("fused", [False, True], ids=["unfused", "fused"])
+@pytest.mark.parametrize("name", sorted(MODULE_CASES))
+def test_module_on_gpu_matches_reference_module(name, fused, cuda_device):
+    msda.load_ops()
+    if fused:
+        cfg, state, x = module_case(name)
+        dims_ok = cfg["n_levels"] * cfg["n_points"] <= 32
+        assert dims_ok
+    compare(run_module(name, cuda_device, torch.float32, fused=fused, tracing=False), name, 2e-4)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ref_dim", [2, 4])
+@pytest.mark.parametrize("dtype,rtol", [(torch.float32, 1e-4), (torch.bfloat16, 2e-2)], ids=["f32", "bf16"])
+def test_fused_function_equals_unfused_composition(ref_dim, dtype, rtol, cuda_device):
+    """MSDeformAttnFusedFunction == softmax + location arithmetic (eager torch) + MSDeformAttnFunction, fwd and all grads,
+    on a COCO-shaped call (decoder: Lq=300 on the 800x1333 pyramid)."""
+    msda.load_ops()
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(5)
+    levels = ((100, 167), (50, 84), (25, 42), (13, 21))
+    N, Lq, M, D, L, P = 2, 300, 8, 32, 4, 4
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    rnd = lambda *s: torch.rand(*s, device=dev, generator=g)
+    value = ((rnd(N, S, M, D) - 0.5)).to(dtype)
+    ref = rnd(N, Lq, L, 2)
+    if ref_dim == 4:
+        ref = torch.cat([ref, rnd(N, Lq, L, 2) * 0.3], -1)
+    ref = ref.to(dtype)
+    off = ((rnd(N, Lq, M, L, P, 2) - 0.5) * 8).to(dtype)
+    logits = ((rnd(N, Lq, M, L * P) - 0.5) * 4).to(dtype)
+    go = (rnd(N, Lq, M * D) - 0.5).to(dtype)
+
+    def leaves():
+        return [t.detach().clone().requires_grad_(True) for t in (value, ref, off, logits)]
+
+    v1, r1, o1, l1 = leaves()
+    out1 = msda.MSDeformAttnFusedFunction.apply(v1, shapes, start, r1, o1, l1)
+    out1.backward(go)
+    # composition in float32 on the SAME (possibly bf16-rounded) inputs = what the fused kernel computes internally
+    v2, r2, o2, l2 = [t.float().detach().requires_grad_(True) for t in (value, ref, off, logits)]
+    attn = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = r2[:, :, None, :, None, :] + o2 / norm[None, None, None, :, None, :]
+    else:
+        loc = r2[:, :, None, :, None, :2] + o2 / P * r2[:, :, None, :, None, 2:] * 0.5
+    out2 = msda.MSDeformAttnFunction.apply(v2, shapes, start, loc.contiguous(), attn.contiguous(), 64)
+    out2.backward(go.float())
+    f = lambda t: t.detach().double().cpu().numpy()
+    assert_close(f(out1), f(out2), rtol, rtol * rms(f(out2)), "out")
+    for a, b, n in ((v1, v2, "grad_value"), (r1, r2, "grad_ref"), (o1, o2, "grad_offsets"), (l1, l2, "grad_logits")):
+        assert_close(f(a.grad), f(b.grad), rtol, rtol * rms(f(b.grad)), n)

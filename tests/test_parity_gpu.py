@@ -278,3 +278,30 @@ def test_module_matches_its_tracing_path(cuda_device):
         a = mod(q, refp, src, shapes, start, mask)
         b = mod(q, refp, src, shapes, start, mask, is_tracing=None)
         assert torch.allclose(a, b, rtol=1e-4, atol=1e-5), (a - b).abs().max()
+
+
+def test_more_than_2e31_elements_uses_64bit_indexing(cuda_device):
+    """value with > 2^31 elements: the reference indexes with 32-bit `int` (ms_deform_im2col_cuda.cuh:255-271) and
+    overflows; here images are addressed with 64-bit offsets.  The LAST image must give the same rows as that image alone."""
+    free, _ = torch.cuda.mem_get_info()
+    if free < 40e9:
+        pytest.skip("needs ~25 GB of device memory")
+    w = Workload("big", 384, ((100, 167), (50, 84), (25, 42), (13, 21)), 3, M=8, P=4, D=32)  # 384*22223*256 = 2.18e9 > 2^31
+    # (384 = 6 x 64: the reference API demands batch % min(batch, im2col_step) == 0, ms_deform_attn_cuda.cu:50-52)
+    assert w.N * w.S * w.M * w.D > 2**31
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(1)
+    value = torch.rand((w.N, w.S, w.M, w.D), device=dev, generator=g)
+    shapes = torch.tensor(w.levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    loc = torch.rand((w.N, w.Lq, w.M, w.L, w.P, 2), device=dev, generator=g)
+    attn = torch.rand((w.N, w.Lq, w.M, w.L, w.P), device=dev, generator=g)
+    go = torch.rand((w.N, w.Lq, w.M * w.D), device=dev, generator=g)
+    out = msda.ms_deform_attn_forward(value, shapes, start, loc, attn)
+    last = msda.ms_deform_attn_forward(value[-1:].contiguous(), shapes, start, loc[-1:].contiguous(), attn[-1:].contiguous())
+    assert torch.equal(out[-1:], last)
+    gv, gl, ga = msda.ms_deform_attn_backward(value, shapes, start, loc, attn, go)
+    gv1, gl1, ga1 = msda.ms_deform_attn_backward(value[-1:].contiguous(), shapes, start, loc[-1:].contiguous(), attn[-1:].contiguous(), go[-1:].contiguous())
+    assert torch.equal(gl[-1:], gl1) and torch.equal(ga[-1:], ga1)
+    assert torch.allclose(gv[-1:], gv1, rtol=1e-5, atol=1e-6)   # atomics: order of accumulation may differ
+    assert not gv[:-1].isnan().any()
