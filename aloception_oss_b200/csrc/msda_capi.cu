@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -63,7 +63,11 @@ bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) %
 
 struct Launch {
   dim3 grid, block;
+  int head_major = 0;
 };
+
+// knob: 0 = auto, 1 = force unit-major, 2 = force head-major
+int head_major_for(const msda_dims& d);
 
 // one warp per (b, q, m) unit
 Launch unit_launch(long long units, int default_warps) {
@@ -86,7 +90,11 @@ Launch image_launch(const msda_dims& d, int default_warps) {
   }
   Launch l;
   l.block = dim3(32 * wpb);
-  l.grid = dim3((unsigned)((qm + wpb - 1) / wpb), (unsigned)d.batch);
+  l.head_major = head_major_for(d);
+  if (l.head_major)  // CTA = one head x wpb consecutive queries
+    l.grid = dim3((unsigned)(((long long)d.num_query + wpb - 1) / wpb * d.num_heads), (unsigned)d.batch);
+  else
+    l.grid = dim3((unsigned)((qm + wpb - 1) / wpb), (unsigned)d.batch);
   return l;
 }
 
@@ -95,6 +103,13 @@ bool vec_shape_ok(const msda_dims& d) {
   return !g_force_generic.load(std::memory_order_relaxed) && d.batch <= 65535 && d.num_point < (1 << 15) &&
          (long long)d.spatial_size * d.num_heads * d.channels <= (1LL << 27) &&
          (long long)d.num_query * d.num_heads < (1LL << 31) - 64;
+}
+
+int head_major_for(const msda_dims& d) {
+  const int k = g_head_major.load(std::memory_order_relaxed);
+  if (k == 1) return 0;
+  if (k == 2) return 1;
+  return 0;
 }
 
 int pick_unroll(int knob, int fallback) {
@@ -114,7 +129,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
 #define MSDA_FWD(UU)                                                                                          \
   msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED><<<l.grid, l.block, 0, st>>>(                                  \
       (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
-      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim)
+      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major)
   if (U == 1) MSDA_FWD(1); else if (U == 2) MSDA_FWD(2); else MSDA_FWD(4);
 #undef MSDA_FWD
   return check_launch(FUSED ? "msda_fused_forward" : "msda_forward(vector)");
@@ -197,10 +212,11 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   const T* go_ = (const T*)go; const T* value_ = (const T*)value; const T* loc_ = (const T*)loc; const T* attn_ = (const T*)attn;
   T* gloc_ = (T*)gloc; T* gattn_ = (T*)gattn; const T* ref_ = (const T*)ref;
   const int S = d.spatial_size, M = d.num_heads, L = d.num_levels, P = d.num_point, QM = d.num_query * d.num_heads;
+  const int hm = l.head_major;
   cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
   e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED>, go_, value_, shapes, start, loc_, attn_, \
-                         gv, gloc_, gattn_, S, M, L, P, inv_p, QM, ref_, ref_dim, gref)
+                         gv, gloc_, gattn_, S, M, L, P, inv_p, QM, ref_, ref_dim, gref, hm)
   if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4);
 #undef MSDA_BWD
   g_launches.fetch_add(1, std::memory_order_relaxed);
@@ -353,6 +369,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "bwd_unroll")) return &g_bwd_unroll;
   if (!strcmp(name, "warps_per_block")) return &g_warps_per_block;
   if (!strcmp(name, "no_pdl")) return &g_no_pdl;
+  if (!strcmp(name, "head_major")) return &g_head_major;
   return nullptr;
 }
 

@@ -20,7 +20,7 @@
 #include <stdint.h>
 
 #ifndef MSDA_MAX_THREADS
-#define MSDA_MAX_THREADS 128  // warps_per_block <= 4 (2 is the default: small CTAs fill the SMs evenly)
+#define MSDA_MAX_THREADS 256  // warps_per_block <= 8
 #endif
 
 namespace msda {
@@ -135,6 +135,39 @@ template <> struct Vec16<__half> {
     return make_uint4(w[0], w[1], w[2], w[3]);
   }
 };
+
+// Gather granule of the BACKWARD kernel: VB bytes per lane.  fp32 uses 16 (4 channels / lane, 8 lanes per 128-B row).
+// The 16-bit types use 8 bytes (4 channels / lane, 8 lanes per 64-B row) there, so that the 8 lanes of a row write
+// 8 x 16 B = 128 CONTIGUOUS bytes of the fp32 grad_value image per `red.v4.f32` instruction.  With 16-byte gathers a
+// lane owns 8 channels = two separate 16-B pieces, every red instruction half-fills its 32-B sectors, and the L2 does
+// twice the atomic sector operations (measured: bf16 backward 1.8x SLOWER than fp32 -- profiles/).
+template <typename T, int VB> struct VecIO;
+template <typename T> struct VecIO<T, 16> {
+  static constexpr int N = Vec16<T>::N;
+  using Raw = uint4;
+  __device__ static __forceinline__ Raw load(const void* p) { return __ldg(reinterpret_cast<const uint4*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[N]) { Vec16<T>::unpack(r, f); }
+};
+template <> struct VecIO<__nv_bfloat16, 8> {
+  static constexpr int N = 4;
+  using Raw = uint2;
+  __device__ static __forceinline__ Raw load(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[4]) {
+    f[0] = __uint_as_float(r.x << 16); f[1] = __uint_as_float(r.x & 0xffff0000u);
+    f[2] = __uint_as_float(r.y << 16); f[3] = __uint_as_float(r.y & 0xffff0000u);
+  }
+};
+template <> struct VecIO<__half, 8> {
+  static constexpr int N = 4;
+  using Raw = uint2;
+  __device__ static __forceinline__ Raw load(const void* p) { return __ldg(reinterpret_cast<const uint2*>(p)); }
+  __device__ static __forceinline__ void unpack(const Raw& r, float (&f)[4]) {
+    const float2 a = __half22float2(*reinterpret_cast<const __half2*>(&r.x));
+    const float2 b = __half22float2(*reinterpret_cast<const __half2*>(&r.y));
+    f[0] = a.x; f[1] = a.y; f[2] = b.x; f[3] = b.y;
+  }
+};
+template <typename T> struct BwdGranule { static constexpr int VB = sizeof(T) == 4 ? 16 : 8; };
 
 // (x, y) pair of one sampling location
 __device__ __forceinline__ void load_xy(const float* p, float& x, float& y) {
@@ -293,6 +326,24 @@ __device__ __forceinline__ void tap_pointers(const T* vb, int off, int rsf, int 
   }
 }
 
+// Which (query, head) unit a warp owns.
+//   unit-major (default): consecutive warps = consecutive heads of one query (units are stored in that order);
+//   head-major: a CTA holds ONE head of `warps` consecutive queries -- for raster-ordered queries (encoder
+//   self-attention) neighbouring queries of the same head sample overlapping pixel neighbourhoods, so their taps
+//   hit in the SM's L1 instead of each going to L2.  Pure scheduling: results are identical.
+__device__ __forceinline__ bool unit_of_warp(int M, int QM, int head_major, int& uq, int& m) {
+  const int wpb = blockDim.x >> 5, w = threadIdx.x >> 5;
+  if (head_major) {
+    m = blockIdx.x % M;
+    const int q = (blockIdx.x / M) * wpb + w;
+    uq = q * M + m;
+    return uq < QM;
+  }
+  uq = blockIdx.x * wpb + w;
+  m = uq % M;
+  return uq < QM;
+}
+
 // packed fp32 pairs (sm_100 FFMA2 / FMUL2: two lanes of fp32 math per issue slot)
 __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return __ffma2_rn(make_float2(w, w), v, acc); }
 
@@ -300,15 +351,14 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // VECTOR FORWARD
 // ------------------------------------------------------------------------------------------------
 // Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
-// Register budgets via min-CTAs/SM at 128 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 56 regs (36 warps/SM, keeps the
-// 4 800-unit C2 call in ONE wave), U=4 -> 80 regs (24 warps/SM).
+// Register budgets via min-CTAs/SM at 256 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 64 regs, U=4 -> 80 regs.
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits, `ref` the reference points (last dim RD).
 template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 12 : (U == 2 ? 9 : 6))
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 6 : (U == 2 ? 4 : 3))
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
@@ -317,10 +367,9 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
   const int M = MC > 0 ? MC : Mrt;
   const int MD = M * D;
   const int lane = threadIdx.x & 31;
-  const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);  // unit inside image blockIdx.y
-  if (uq >= QM) return;                                                // warp-uniform
+  int uq, m;  // unit inside image blockIdx.y, its head
+  if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
   const int g = lane / LPR, cl = lane % LPR;
-  const int m = uq % M;
   const int LP = L * P;
   const long long u = (long long)blockIdx.y * QM + uq;
   const T* __restrict__ u_loc = loc + u * (LP * 2);
@@ -412,14 +461,15 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 // location arithmetic differentiated in the kernel), `gref` (fp32, pre-zeroed, may be null) accumulates the gradient
 // w.r.t. the reference points with scalar reds (M*P contributions per element).
 template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 9 : (U == 2 ? 7 : 5))
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 4 : (U == 2 ? 3 : 2))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
                    T* __restrict__ gloc, T* __restrict__ gattn,
                    int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
-                   float* __restrict__ gref) {
-  constexpr int VEC = Vec16<T>::N;
+                   float* __restrict__ gref, int head_major) {
+  using IO = VecIO<T, BwdGranule<T>::VB>;
+  constexpr int VEC = IO::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
@@ -427,10 +477,9 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   const int M = MC > 0 ? MC : Mrt;
   const int MD = M * D;
   const int lane = threadIdx.x & 31;
-  const int uq = blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (uq >= QM) return;  // warp-uniform (an exited warp needs no fence)
+  int uq, m;
+  if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform (an exited warp needs no fence)
   const int g = lane / LPR, cl = lane % LPR;
-  const int m = uq % M;
   const int LP = L * P;
   const long long u = (long long)blockIdx.y * QM + uq;
   const T* __restrict__ u_loc = loc + u * (LP * 2);
@@ -440,7 +489,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   float* __restrict__ gb = gv + voff;
 
   float go[VEC];
-  Vec16<T>::unpack(ldg128(grad_out + u * D + cl * VEC), go);
+  IO::unpack(IO::load(grad_out + u * D + cl * VEC), go);
   bool fenced = false;
 
   for (int base = 0; base < LP; base += 32) {
@@ -476,18 +525,18 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
       const T* tp[U][4];
 #pragma unroll
       for (int j = 0; j < U; ++j) tap_pointers<T>(vb, off[j], rsf[j], MD, all_ok, tp[j]);
-      uint4 v[U][4];
+      typename IO::Raw v[U][4];
 #pragma unroll
       for (int j = 0; j < U; ++j)
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
+        for (int t = 0; t < 4; ++t) v[j][t] = IO::load(tp[j][t]);
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         float d[4];
 #pragma unroll
         for (int t = 0; t < 4; ++t) {
           float f[VEC];
-          Vec16<T>::unpack(v[j][t], f);
+          IO::unpack(v[j][t], f);
           float2 p = make_float2(0.f, 0.f);
 #pragma unroll
           for (int i = 0; i < VEC / 2; ++i) p = __ffma2_rn(make_float2(go[2 * i], go[2 * i + 1]), make_float2(f[2 * i], f[2 * i + 1]), p);

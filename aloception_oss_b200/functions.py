@@ -89,6 +89,29 @@ def _ptr(t):
     return ctypes.c_void_p(t.data_ptr()) if t.numel() else ctypes.c_void_p(0)
 
 
+class _on_device:
+    """``with _on_device(t) as stream_handle``: makes t's GPU current only if it is not already (the common case costs
+    two cheap queries instead of a device-guard round trip) and yields the raw current ``cudaStream_t``."""
+
+    __slots__ = ("idx", "prev")
+
+    def __init__(self, t):
+        self.idx = t.device.index
+        self.prev = None
+
+    def __enter__(self):
+        cur = torch.cuda.current_device()
+        if self.idx is not None and cur != self.idx:
+            self.prev = cur
+            torch.cuda.set_device(self.idx)
+        return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+    def __exit__(self, *exc):
+        if self.prev is not None:
+            torch.cuda.set_device(self.prev)
+        return False
+
+
 def _check_out(t, shape, like, name):
     if tuple(t.shape) != tuple(shape) or t.dtype != like.dtype or t.device != like.device or not t.is_contiguous():
         raise RuntimeError(f"{name} must be a contiguous {like.dtype} tensor of shape {tuple(shape)} on {like.device}")
@@ -104,10 +127,9 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     start = _meta_i32(level_start_index, "level_start_index")
     oshape = (dims.batch, dims.num_query, dims.num_heads * dims.channels)
     out = torch.empty(oshape, dtype=value.dtype, device=value.device) if out is None else _check_out(out, oshape, value, "out")
-    with torch.cuda.device(value.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _on_device(value) as stream:
         rc = _capi.lib().msda_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight),
-                                      _ptr(out), ctypes.byref(dims), _DTYPES[value.dtype], ctypes.c_void_p(stream))
+                                      _ptr(out), ctypes.byref(dims), _DTYPES[value.dtype], stream)
     if rc != 0:
         raise RuntimeError("msda_forward failed: " + _capi.last_error())
     return out
@@ -134,12 +156,11 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     dt = _DTYPES[value.dtype]
     ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _on_device(value) as stream:
         rc = L.msda_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc),
                              _ptr(attn_weight), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
                              _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, ctypes.byref(dims), dt, 0,
-                             ctypes.c_void_p(stream))
+                             stream)
     if rc != 0:
         raise RuntimeError("msda_backward failed: " + _capi.last_error())
     return [grad_value, grad_loc, grad_attn]
@@ -185,11 +206,10 @@ def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, refer
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=value.device)
-    with torch.cuda.device(value.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _on_device(value) as stream:
         rc = _capi.lib().msda_fused_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
                                             _ptr(sampling_offsets), _ptr(attn_logits), _ptr(out), ctypes.byref(dims),
-                                            _DTYPES[value.dtype], ctypes.c_void_p(stream))
+                                            _DTYPES[value.dtype], stream)
     if rc != 0:
         raise RuntimeError("msda_fused_forward failed: " + _capi.last_error())
     return out
@@ -213,13 +233,12 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
     dt = _DTYPES[value.dtype]
     ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
     ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
-    with torch.cuda.device(value.device):
-        stream = torch.cuda.current_stream().cuda_stream
+    with _on_device(value) as stream:
         rc = L.msda_fused_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
                                    _ptr(sampling_offsets), _ptr(attn_logits), _ptr(grad_value), _ptr(grad_off),
                                    _ptr(grad_logits), _ptr(grad_ref) if grad_ref is not None else ctypes.c_void_p(0),
                                    _ptr(ws) if ws is not None else ctypes.c_void_p(0), ws_bytes, ctypes.byref(dims), dt, 0,
-                                   ctypes.c_void_p(stream))
+                                   stream)
     if rc != 0:
         raise RuntimeError("msda_fused_backward failed: " + _capi.last_error())
     if grad_ref is not None and grad_ref.dtype != value.dtype:

@@ -52,7 +52,7 @@ def test_abi_version_and_error_channel():
 
 
 def test_tuning_knobs_roundtrip():
-    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl"):
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major"):
         _capi.set_tuning(k, 3)
         assert _capi.get_tuning(k) == 3
         _capi.set_tuning(k, 0)
