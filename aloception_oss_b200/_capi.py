@@ -12,7 +12,8 @@ import subprocess
 
 _PKG = os.path.dirname(os.path.abspath(__file__))
 ROOT = os.path.dirname(_PKG)
-LIB_PATH = os.path.join(_PKG, "libmsda_b200.so")
+# MSDA_LIB_PATH / MSDA_NVCC_EXTRA: build or load an experimental variant next to the product library (tuning only)
+LIB_PATH = os.environ.get("MSDA_LIB_PATH") or os.path.join(_PKG, "libmsda_b200.so")
 CSRC = os.path.join(_PKG, "csrc")
 HEADER = os.path.join(ROOT, "include", "msda_b200.h")
 
@@ -49,7 +50,8 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     if not force and not needs_build():
         return LIB_PATH
     nvcc = shutil.which("nvcc") or "/usr/local/cuda/bin/nvcc"
-    cmd = [nvcc] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
+    extra = os.environ.get("MSDA_NVCC_EXTRA", "").split()
+    cmd = [nvcc] + NVCC_FLAGS + extra + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB_PATH] + sources()
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)

@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -112,6 +112,15 @@ int head_major_for(const msda_dims& d) {
   return 0;
 }
 
+// forward kernel: sample records through shared memory instead of shuffles?
+// Measured (profiles/r1_sweep_smem_records.jsonl): fp32 gains 1-5 % everywhere (encoder shapes most: SHFL shares the
+// L1 data pipe with the returning tap rows); 16-bit rows gain on one-wave decoder calls (C2 bf16 5.2 -> 4.7 us) and lose
+// ~4 % on multi-wave encoder calls, where the two extra CTA-resident kilobytes cost more L1 than the shuffles did.
+bool smem_records_auto(const msda_dims& d, size_t elt) {
+  if (elt == 4) return true;
+  return (long long)d.batch * d.num_query * d.num_heads <= 148LL * 36;
+}
+
 int pick_unroll(int knob, int fallback) {
   const int u = knob;
   return (u == 1 || u == 2 || u == 4) ? u : fallback;
@@ -126,11 +135,15 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
-#define MSDA_FWD(UU)                                                                                          \
-  msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED><<<l.grid, l.block, 0, st>>>(                                  \
+  // records through shared memory (24 B / thread) or through shuffles: knob "smem_records" 0 = auto, 1 = shuffles, 2 = smem
+  const int srk = g_smem_records.load(std::memory_order_relaxed);
+  const bool sr = U == 1 && (srk == 2 || (srk == 0 && smem_records_auto(d, sizeof(T))));
+#define MSDA_FWD(UU, SR)                                                                                      \
+  msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED, SR><<<l.grid, l.block, SR ? 24 * l.block.x : 0, st>>>(        \
       (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
       d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major)
-  if (U == 1) MSDA_FWD(1); else if (U == 2) MSDA_FWD(2); else MSDA_FWD(4);
+  if (U == 1) { if (sr) MSDA_FWD(1, true); else MSDA_FWD(1, false); }
+  else if (U == 2) MSDA_FWD(2, false); else MSDA_FWD(4, false);
 #undef MSDA_FWD
   return check_launch(FUSED ? "msda_fused_forward" : "msda_forward(vector)");
 }
@@ -370,6 +383,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "warps_per_block")) return &g_warps_per_block;
   if (!strcmp(name, "no_pdl")) return &g_no_pdl;
   if (!strcmp(name, "head_major")) return &g_head_major;
+  if (!strcmp(name, "smem_records")) return &g_smem_records;
   return nullptr;
 }
 

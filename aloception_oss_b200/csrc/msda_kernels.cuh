@@ -22,6 +22,9 @@
 #ifndef MSDA_MAX_THREADS
 #define MSDA_MAX_THREADS 256  // warps_per_block <= 8
 #endif
+#ifndef MSDA_FWD_MIN_CTAS  // min resident 256-thread CTAs per SM of the U=1 forward kernel: 6 -> 40 registers, 5 -> 48
+#define MSDA_FWD_MIN_CTAS 6
+#endif
 
 namespace msda {
 
@@ -168,6 +171,63 @@ template <> struct VecIO<__half, 8> {
   }
 };
 template <typename T> struct BwdGranule { static constexpr int VB = sizeof(T) == 4 ? 16 : 8; };
+
+// Store N consecutive accumulators as T (N * sizeof(T) in {2, 4, 8, 16} bytes, naturally aligned).
+template <typename T, int N>
+__device__ __forceinline__ void store_vals(T* p, const float (&r)[N]) {
+  if constexpr (N * sizeof(T) == 16) {
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<uint4*>(p) = make_uint4(__float_as_uint(r[0]), __float_as_uint(r[1]), __float_as_uint(r[2]), __float_as_uint(r[3]));
+    } else {
+      float f[8];
+#pragma unroll
+      for (int i = 0; i < 8; ++i) f[i] = r[i];
+      *reinterpret_cast<uint4*>(p) = Vec16<T>::pack(f);
+    }
+  } else {
+#pragma unroll
+    for (int i = 0; i < N; ++i) p[i] = from_acc<T>(r[i]);  // ptxas merges these into one 32/64-bit store where it can
+  }
+}
+
+// Sum r[] over the G = 32/LPR lane groups of a warp (lane = g*LPR + cl) and leave the result SCATTERED: every
+// step a lane keeps one half of its values and trades the other half with its partner group (butterfly
+// reduce-scatter), so the warp moves VEC-1 values per lane instead of VEC*log2(G) (3 vs 8 shuffles for fp32 D=32,
+// 7 vs 24 for bf16 D=32 -- SHFL shares the L1 data pipe with the tap loads, profiles/).  Same pairs are added in the
+// same order as a plain xor-butterfly: results are bit-identical.  On return the lane holds `n` sums starting at
+// channel `first` of its VEC-channel slice; `owner` is false on lanes holding a duplicate (G > VEC).
+template <int VEC, int LPR>
+struct GroupReduceScatter {
+  static constexpr int G = 32 / LPR;
+  static constexpr int STEPS_HALVING = (G >= VEC) ? (VEC == 1 ? 0 : (VEC == 2 ? 1 : (VEC == 4 ? 2 : 3)))
+                                                  : (G == 1 ? 0 : (G == 2 ? 1 : (G == 4 ? 2 : (G == 8 ? 3 : 4))));
+  static constexpr int N_OUT = VEC >> STEPS_HALVING;
+};
+
+template <int N, int O, int LPR>
+__device__ __forceinline__ void reduce_scatter_steps(float (&r)[N], int lane, int& first, bool& owner) {
+  if constexpr (O < 32) {
+    if constexpr (N > 1) {
+      constexpr int H = N / 2;
+      const bool upper = (lane & O) != 0;
+      float k[H];
+#pragma unroll
+      for (int i = 0; i < H; ++i) {
+        const float send = upper ? r[i] : r[H + i];
+        const float keep = upper ? r[H + i] : r[i];
+        k[i] = keep + __shfl_xor_sync(0xffffffffu, send, O);
+      }
+      if (upper) first += H;
+      reduce_scatter_steps<H, O * 2, LPR>(k, lane, first, owner);
+#pragma unroll
+      for (int i = 0; i < H; ++i) r[i] = k[i];
+    } else {
+      r[0] += __shfl_xor_sync(0xffffffffu, r[0], O);
+      if (lane & O) owner = false;
+      reduce_scatter_steps<1, O * 2, LPR>(r, lane, first, owner);
+    }
+  }
+}
 
 // (x, y) pair of one sampling location
 __device__ __forceinline__ void load_xy(const float* p, float& x, float& y) {
@@ -353,8 +413,11 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
 // Register budgets via min-CTAs/SM at 256 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 64 regs, U=4 -> 80 regs.
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits, `ref` the reference points (last dim RD).
-template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 6 : (U == 2 ? 4 : 3))
+// SR: the per-sample records travel from the geometry lanes to the lane groups through a warp-private slice of
+// shared memory (2 broadcast LDS per round, one wavefront each) instead of 6 SHFL per round (one wavefront each on
+// the same L1 data pipe the tap rows return through).  Dynamic shared memory: 24 bytes per thread.
+template <typename T, int D, int MC, int U, bool FUSED, bool SR>
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? MSDA_FWD_MIN_CTAS : (U == 2 ? 4 : 3))
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
@@ -380,6 +443,10 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 #pragma unroll
   for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
 
+  extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
+  uint4* rec_a = reinterpret_cast<uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);  // this warp's 32 records
+  float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
+
   for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
     SampleGeo sg;
     Geo<float> ge;
@@ -396,31 +463,57 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
     const float a = sp.a;
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
+    if constexpr (SR) {
+      if (base > 0) __syncwarp();  // the previous pass has finished reading the records
+      rec_a[lane] = make_uint4((unsigned)sg.off00, (unsigned)sg.rsf, __float_as_uint(w00), __float_as_uint(w01));
+      rec_b[lane] = make_float2(w10, w11);
+      __syncwarp();
+    }
     for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
       int off[U], rsf[U];
       float w[U][4];
       bool full = true;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int src = k0 + j * G + g;
-        off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
-        rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
-        w[j][0] = __shfl_sync(0xffffffffu, w00, src);
-        w[j][1] = __shfl_sync(0xffffffffu, w01, src);
-        w[j][2] = __shfl_sync(0xffffffffu, w10, src);
-        w[j][3] = __shfl_sync(0xffffffffu, w11, src);
-        if (src >= cnt) rsf[j] = 0;  // shfl wraps modulo 32: a lane group past the end must not gather
+        const int src = k0 + j * G + g;  // < 32: G * U divides 32
+        if constexpr (SR) {
+          const uint4 ra = rec_a[src];
+          const float2 rb = rec_b[src];
+          off[j] = (int)ra.x;
+          rsf[j] = (int)ra.y;
+          w[j][0] = __uint_as_float(ra.z);
+          w[j][1] = __uint_as_float(ra.w);
+          w[j][2] = rb.x;
+          w[j][3] = rb.y;
+        } else {
+          off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
+          rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
+          w[j][0] = __shfl_sync(0xffffffffu, w00, src);
+          w[j][1] = __shfl_sync(0xffffffffu, w01, src);
+          w[j][2] = __shfl_sync(0xffffffffu, w10, src);
+          w[j][3] = __shfl_sync(0xffffffffu, w11, src);
+        }
+        if (src >= cnt) rsf[j] = 0;  // a lane group past the end must not gather
         full = full && ((rsf[j] & 15) == 15);
       }
       const bool all_ok = __all_sync(0xffffffffu, full);
-      const T* tp[U][4];
-#pragma unroll
-      for (int j = 0; j < U; ++j) tap_pointers<T>(vb, off[j], rsf[j], MD, all_ok, tp[j]);
       uint4 v[U][4];
+      if (all_ok) {  // loads duplicated per branch: here the x+1 taps are immediate offsets of the x taps
 #pragma unroll
-      for (int j = 0; j < U; ++j)
+        for (int j = 0; j < U; ++j) {
+          const T* t0 = vb + off[j];
+          const T* t1 = vb + (off[j] + (rsf[j] >> 4));  // one IMAD.WIDE per pointer
+          v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + MD); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + MD);
+        }
+      } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[j][t]);
+        for (int j = 0; j < U; ++j) {
+          const T* tp[4];
+          tap_pointers<T>(vb, off[j], rsf[j], MD, false, tp);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[t]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < U; ++j)
 #pragma unroll
@@ -435,11 +528,16 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
   float r[VEC];
 #pragma unroll
   for (int i = 0; i < VEC / 2; ++i) { r[2 * i] = acc[i].x; r[2 * i + 1] = acc[i].y; }
+  int first = 0;
+  bool owner = true;
+  reduce_scatter_steps<VEC, LPR, LPR>(r, lane, first, owner);
+  constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
+  if (owner) {
+    float o[N_OUT];
 #pragma unroll
-  for (int o = LPR; o < 32; o <<= 1)
-#pragma unroll
-    for (int i = 0; i < VEC; ++i) r[i] += __shfl_xor_sync(0xffffffffu, r[i], o);
-  if (g == 0) *reinterpret_cast<uint4*>(out + u * D + cl * VEC) = Vec16<T>::pack(r);
+    for (int i = 0; i < N_OUT; ++i) o[i] = r[i];
+    store_vals<T, N_OUT>(out + u * D + cl * VEC + first, o);
+  }
 }
 
 // ------------------------------------------------------------------------------------------------
@@ -522,14 +620,23 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         full = full && ((rsf[j] & 15) == 15);
       }
       const bool all_ok = __all_sync(0xffffffffu, full);
-      const T* tp[U][4];
-#pragma unroll
-      for (int j = 0; j < U; ++j) tap_pointers<T>(vb, off[j], rsf[j], MD, all_ok, tp[j]);
       typename IO::Raw v[U][4];
+      if (all_ok) {  // loads duplicated per branch: here the x+1 taps are immediate offsets of the x taps
 #pragma unroll
-      for (int j = 0; j < U; ++j)
+        for (int j = 0; j < U; ++j) {
+          const T* t0 = vb + off[j];
+          const T* t1 = t0 + (rsf[j] >> 4);
+          v[j][0] = IO::load(t0); v[j][1] = IO::load(t0 + MD); v[j][2] = IO::load(t1); v[j][3] = IO::load(t1 + MD);
+        }
+      } else {
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[j][t] = IO::load(tp[j][t]);
+        for (int j = 0; j < U; ++j) {
+          const T* tp[4];
+          tap_pointers<T>(vb, off[j], rsf[j], MD, false, tp);
+#pragma unroll
+          for (int t = 0; t < 4; ++t) v[j][t] = IO::load(tp[t]);
+        }
+      }
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         float d[4];

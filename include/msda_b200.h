@@ -132,6 +132,7 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
  *   "warps_per_block"  0=auto, 1..4 (vector kernels), 1..8 (generic kernels)
  *   "no_pdl"           0|1   launch the backward kernel without programmatic dependent launch
  *   "head_major"       0=auto, 1=unit-major CTAs, 2=head-major CTAs (one head x consecutive queries per CTA)
+ *   "smem_records"     0=auto, 1=per-sample records broadcast with warp shuffles, 2=through shared memory (forward)
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

@@ -22,7 +22,7 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _ops(cuda_device):
     msda.load_ops()
-    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major"):
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -127,7 +127,8 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 @pytest.mark.parametrize("w", [SHAPES[0], SHAPES[1], SHAPES[9]], ids=lambda w: w.name)
 @pytest.mark.parametrize("no_pdl", [0, 1])
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
-                                      ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2)])
+                                      ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2),
+                                      ("smem_records", 1), ("smem_records", 2)])
 def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)

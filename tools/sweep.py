@@ -50,6 +50,9 @@ def main():
     ap.add_argument("--wpbs", default="2,4,8")
     ap.add_argument("--no-pdl", default="0")
     ap.add_argument("--head-major", default="1")
+    ap.add_argument("--smem-records", default="0")
+    ap.add_argument("--tag", default="")
+    ap.add_argument("--no-generic", action="store_true")
     ap.add_argument("--max-sets", type=int, default=24)
     args = ap.parse_args()
     msda.load_ops()
@@ -71,7 +74,8 @@ def main():
             sets = [device_inputs(w, seed=5 + i, device=dev, dtype=tdt, loc_mode=mode) for i in range(n_sets)]
             fwd = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
             bwd = lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
-            for hm, var, u, wpb in itertools.product([int(x) for x in args.head_major.split(",")], [int(x) for x in args.no_pdl.split(",")], [int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+            for sr, hm, var, u, wpb in itertools.product([int(x) for x in args.smem_records.split(",")], [int(x) for x in args.head_major.split(",")], [int(x) for x in args.no_pdl.split(",")], [int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+                _capi.set_tuning("smem_records", sr)
                 _capi.set_tuning("head_major", hm)
                 _capi.set_tuning("no_pdl", var)
                 _capi.set_tuning("warps_per_block", wpb)
@@ -79,13 +83,18 @@ def main():
                 _capi.set_tuning("bwd_unroll", u)
                 tf = time_graph(fwd, sets)
                 tb = time_graph(bwd, sets)
-                rec = dict(workload=name, dtype=args.dtype, loc=mode, sets=n_sets, no_pdl=var, head_major=hm, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
+                rec = dict(tag=args.tag, workload=name, dtype=args.dtype, loc=mode, sets=n_sets, no_pdl=var, head_major=hm, smem_records=sr, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
                            fwd_frac=round(w.algorithmic_bytes(elt, False) / tf / 1e3 / peak, 4),
                            bwd_frac=round(w.algorithmic_bytes(elt, True) / tb / 1e3 / peak, 4),
                            fwd_gsps=round(w.samples / tf / 1e3, 3), bwd_gsps=round(w.samples / tb / 1e3, 3))
                 print(json.dumps(rec), flush=True)
                 f.write(json.dumps(rec) + "\n")
             _capi.set_tuning("head_major", 0)
+            _capi.set_tuning("smem_records", 0)
+            if args.no_generic:
+                del sets
+                torch.cuda.empty_cache()
+                continue
             _capi.set_tuning("force_generic", 1)
             tf = time_graph(fwd, sets)
             tb = time_graph(bwd, sets)
