@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -121,6 +121,12 @@ bool smem_records_auto(const msda_dims& d, size_t elt) {
   return (long long)d.batch * d.num_query * d.num_heads <= 148LL * 36;
 }
 
+// forward: patch-ordered persistent kernel?  Only pays when the queries are the pixels of the pyramid (Lq == S).
+bool patch_mode_auto(const msda_dims& d) {
+  (void)d;
+  return false;
+}
+
 int pick_unroll(int knob, int fallback) {
   const int u = knob;
   return (u == 1 || u == 2 || u == 4) ? u : fallback;
@@ -135,6 +141,25 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+  // patch-ordered persistent kernel for pixel-aligned queries (knob "patch_mode": 0 = auto, 1 = off, 2 = on)
+  const int pmk = g_patch_mode.load(std::memory_order_relaxed);
+  if (d.num_levels * d.num_point <= 32 && (pmk == 2 || (pmk == 0 && patch_mode_auto(d)))) {  // one sample per lane
+    int py = g_patch_py.load(std::memory_order_relaxed), px = g_patch_px.load(std::memory_order_relaxed);
+    if (py <= 0 || py > MSDA_PATCH_MAX_THREADS / 32) py = 16;
+    if (px <= 0) px = 8;
+    int ctas = g_patch_ctas.load(std::memory_order_relaxed);
+    if (ctas <= 0) ctas = 1024 / (32 * py);  // 32 warps per SM (the kernel is compiled for <= 64 registers)
+    const int srk2 = g_smem_records.load(std::memory_order_relaxed);
+    const bool sr2 = srk2 == 2 || (srk2 == 0 && sizeof(T) == 4);
+    const dim3 grid((unsigned)(148 * ctas)), block((unsigned)(32 * py));
+#define MSDA_FWDP(SR)                                                                                          \
+  msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR><<<grid, block, SR ? 24 * block.x : 0, st>>>(                \
+      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size,         \
+      d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px)
+    if (sr2) MSDA_FWDP(true); else MSDA_FWDP(false);
+#undef MSDA_FWDP
+    return check_launch(FUSED ? "msda_fused_forward(patch)" : "msda_forward(patch)");
+  }
   // records through shared memory (24 B / thread) or through shuffles: knob "smem_records" 0 = auto, 1 = shuffles, 2 = smem
   const int srk = g_smem_records.load(std::memory_order_relaxed);
   const bool sr = U == 1 && (srk == 2 || (srk == 0 && smem_records_auto(d, sizeof(T))));
@@ -384,6 +409,10 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "no_pdl")) return &g_no_pdl;
   if (!strcmp(name, "head_major")) return &g_head_major;
   if (!strcmp(name, "smem_records")) return &g_smem_records;
+  if (!strcmp(name, "patch_mode")) return &g_patch_mode;
+  if (!strcmp(name, "patch_px")) return &g_patch_px;
+  if (!strcmp(name, "patch_py")) return &g_patch_py;
+  if (!strcmp(name, "patch_ctas")) return &g_patch_ctas;
   return nullptr;
 }
 

@@ -364,6 +364,65 @@ __device__ __forceinline__ SampleParams fused_params(const T* __restrict__ u_off
   return p;
 }
 
+// ---- the same two loaders split into "memory" and "arithmetic" halves, so that a warp that walks several units (the
+// patch-ordered forward) can issue the loads of its NEXT unit before the gathers of the current one ----
+struct LevelMeta { int H, W, st, l; };
+struct RawSample { float x, y, a, rx, ry, rw, rh; };  // plain: (x, y) = location, a = weight; FUSED: offsets, logit, reference point
+
+__device__ __forceinline__ LevelMeta load_level_meta(const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                                                     int s, bool have, float inv_p) {
+  LevelMeta lm;
+  lm.l = have ? level_of(s, inv_p) : 0;
+  lm.H = __ldg(shapes + 2 * lm.l);
+  lm.W = __ldg(shapes + 2 * lm.l + 1);
+  lm.st = __ldg(start + lm.l);
+  return lm;
+}
+
+template <typename T, bool FUSED>
+__device__ __forceinline__ RawSample load_raw(const T* __restrict__ u_loc, const T* __restrict__ u_att,
+                                              const T* __restrict__ ref_q, int RD, int s, bool have, int l) {
+  RawSample r;
+  const int si = have ? s : 0;
+  load_xy(u_loc + 2 * si, r.x, r.y);
+  r.rx = r.ry = r.rw = r.rh = 0.f;
+  if constexpr (FUSED) {
+    r.a = have ? load_s(u_att + si) : -INFINITY;
+    r.rx = load_s(ref_q + l * RD);
+    r.ry = load_s(ref_q + l * RD + 1);
+    if (RD != 2) {
+      r.rw = load_s(ref_q + l * RD + 2);
+      r.rh = load_s(ref_q + l * RD + 3);
+    }
+  } else {
+    r.a = load_s(u_att + si);
+  }
+  return r;
+}
+
+// same operation order / roundings as load_params / fused_params
+template <bool FUSED>
+__device__ __forceinline__ SampleParams params_from_raw(const RawSample& r, const LevelMeta& lm, int RD, int P, bool have) {
+  SampleParams p;
+  p.H = lm.H; p.W = lm.W; p.st = lm.st;
+  if constexpr (!FUSED) {
+    p.lx = r.x; p.ly = r.y; p.a = r.a;
+  } else {
+    if (RD == 2) {
+      p.lx = __fadd_rn(r.rx, __fdiv_rn(r.x, (float)p.W));
+      p.ly = __fadd_rn(r.ry, __fdiv_rn(r.y, (float)p.H));
+    } else {
+      p.lx = __fadd_rn(r.rx, __fmul_rn(__fmul_rn(__fdiv_rn(r.x, (float)P), r.rw), 0.5f));
+      p.ly = __fadd_rn(r.ry, __fmul_rn(__fmul_rn(__fdiv_rn(r.y, (float)P), r.rh), 0.5f));
+    }
+    const float mx = warp_max(r.a);
+    const float e = have ? expf(r.a - mx) : 0.f;
+    const float sum = warp_sum(e);
+    p.a = __fdiv_rn(e, sum);
+  }
+  return p;
+}
+
 __device__ __forceinline__ void finish_geometry(const SampleParams& p, bool have, int MD, SampleGeo& sg, Geo<float>& ge) {
   ge = make_geo<float>(p.lx, p.ly, p.H, p.W, have);
   sg.off00 = (p.st + ge.row00) * MD;
@@ -416,115 +475,95 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // SR: the per-sample records travel from the geometry lanes to the lane groups through a warp-private slice of
 // shared memory (2 broadcast LDS per round, one wavefront each) instead of 6 SHFL per round (one wavefront each on
 // the same L1 data pipe the tap rows return through).  Dynamic shared memory: 24 bytes per thread.
-template <typename T, int D, int MC, int U, bool FUSED, bool SR>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? MSDA_FWD_MIN_CTAS : (U == 2 ? 4 : 3))
-msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
-                   const int32_t* __restrict__ start, const T* __restrict__ loc,
-                   const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major) {
+// Gather + reduce + store of one pass (<= 32 samples, one per lane) of one unit, given the lane's sample parameters.
+// `acc` carries the partial sums across passes.
+template <typename T, int D, int U, bool SR>
+__device__ __forceinline__ void
+msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have, int MD, int cnt, float2 (&acc)[Vec16<T>::N / 2]) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
-  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
-
-  const int M = MC > 0 ? MC : Mrt;
-  const int MD = M * D;
   const int lane = threadIdx.x & 31;
-  int uq, m;  // unit inside image blockIdx.y, its head
-  if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
-  const int g = lane / LPR, cl = lane % LPR;
-  const int LP = L * P;
-  const long long u = (long long)blockIdx.y * QM + uq;
-  const T* __restrict__ u_loc = loc + u * (LP * 2);
-  const T* __restrict__ u_att = attn + u * LP;
-  const T* __restrict__ vb = value + (long long)blockIdx.y * S * MD + (m * D + cl * VEC);
-
-  float2 acc[VEC / 2];
-#pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
-
+  const int g = lane / LPR;
   extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
   uint4* rec_a = reinterpret_cast<uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);  // this warp's 32 records
   float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
 
-  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
-    SampleGeo sg;
-    Geo<float> ge;
-    SampleParams sp;
-    const bool have = base + lane < LP;
-    if constexpr (FUSED) {
-      int l;
-      float odx, ody;
-      sp = fused_params<T>(u_loc, u_att, ref + ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
-    } else {
-      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+  SampleGeo sg;
+  Geo<float> ge;
+  finish_geometry(sp, have, MD, sg, ge);
+  const float a = sp.a;
+  const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
+  if constexpr (SR) {
+    __syncwarp();  // the previous pass / the previous unit of this warp has finished reading the records
+    rec_a[lane] = make_uint4((unsigned)sg.off00, (unsigned)sg.rsf, __float_as_uint(w00), __float_as_uint(w01));
+    rec_b[lane] = make_float2(w10, w11);
+    __syncwarp();
+  }
+  for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
+    int off[U], rsf[U];
+    float w[U][4];
+    bool full = true;
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int src = k0 + j * G + g;  // < 32: G * U divides 32
+      if constexpr (SR) {
+        const uint4 ra = rec_a[src];
+        const float2 rb = rec_b[src];
+        off[j] = (int)ra.x;
+        rsf[j] = (int)ra.y;
+        w[j][0] = __uint_as_float(ra.z);
+        w[j][1] = __uint_as_float(ra.w);
+        w[j][2] = rb.x;
+        w[j][3] = rb.y;
+      } else {
+        off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
+        rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
+        w[j][0] = __shfl_sync(0xffffffffu, w00, src);
+        w[j][1] = __shfl_sync(0xffffffffu, w01, src);
+        w[j][2] = __shfl_sync(0xffffffffu, w10, src);
+        w[j][3] = __shfl_sync(0xffffffffu, w11, src);
+      }
+      if (src >= cnt) rsf[j] = 0;  // a lane group past the end must not gather
+      full = full && ((rsf[j] & 15) == 15);
     }
-    finish_geometry(sp, have, MD, sg, ge);
-    const float a = sp.a;
-    const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
-    const int cnt = min(32, LP - base);
-    if constexpr (SR) {
-      if (base > 0) __syncwarp();  // the previous pass has finished reading the records
-      rec_a[lane] = make_uint4((unsigned)sg.off00, (unsigned)sg.rsf, __float_as_uint(w00), __float_as_uint(w01));
-      rec_b[lane] = make_float2(w10, w11);
-      __syncwarp();
-    }
-    for (int k0 = 0; k0 < cnt; k0 += G * U) {  // warp-uniform trip count
-      int off[U], rsf[U];
-      float w[U][4];
-      bool full = true;
+    const bool all_ok = __all_sync(0xffffffffu, full);
+    uint4 v[U][4];
+    if (all_ok) {  // loads duplicated per branch: here the x+1 taps are immediate offsets of the x taps
 #pragma unroll
       for (int j = 0; j < U; ++j) {
-        const int src = k0 + j * G + g;  // < 32: G * U divides 32
-        if constexpr (SR) {
-          const uint4 ra = rec_a[src];
-          const float2 rb = rec_b[src];
-          off[j] = (int)ra.x;
-          rsf[j] = (int)ra.y;
-          w[j][0] = __uint_as_float(ra.z);
-          w[j][1] = __uint_as_float(ra.w);
-          w[j][2] = rb.x;
-          w[j][3] = rb.y;
-        } else {
-          off[j] = __shfl_sync(0xffffffffu, sg.off00, src);
-          rsf[j] = __shfl_sync(0xffffffffu, sg.rsf, src);
-          w[j][0] = __shfl_sync(0xffffffffu, w00, src);
-          w[j][1] = __shfl_sync(0xffffffffu, w01, src);
-          w[j][2] = __shfl_sync(0xffffffffu, w10, src);
-          w[j][3] = __shfl_sync(0xffffffffu, w11, src);
-        }
-        if (src >= cnt) rsf[j] = 0;  // a lane group past the end must not gather
-        full = full && ((rsf[j] & 15) == 15);
+        const T* t0 = vb + off[j];
+        const T* t1 = vb + (off[j] + (rsf[j] >> 4));  // one IMAD.WIDE per pointer
+        v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + MD); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + MD);
       }
-      const bool all_ok = __all_sync(0xffffffffu, full);
-      uint4 v[U][4];
-      if (all_ok) {  // loads duplicated per branch: here the x+1 taps are immediate offsets of the x taps
+    } else {
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const T* t0 = vb + off[j];
-          const T* t1 = vb + (off[j] + (rsf[j] >> 4));  // one IMAD.WIDE per pointer
-          v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + MD); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + MD);
-        }
-      } else {
+      for (int j = 0; j < U; ++j) {
+        const T* tp[4];
+        tap_pointers<T>(vb, off[j], rsf[j], MD, false, tp);
 #pragma unroll
-        for (int j = 0; j < U; ++j) {
-          const T* tp[4];
-          tap_pointers<T>(vb, off[j], rsf[j], MD, false, tp);
-#pragma unroll
-          for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[t]);
-        }
+        for (int t = 0; t < 4; ++t) v[j][t] = ldg128(tp[t]);
       }
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float f[VEC];
-          Vec16<T>::unpack(v[j][t], f);
-#pragma unroll
-          for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
-        }
     }
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float f[VEC];
+        Vec16<T>::unpack(v[j][t], f);
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
+      }
   }
+}
+
+// sum the lane groups' partial sums and write the unit's D outputs
+template <typename T, int D>
+__device__ __forceinline__ void msda_fwd_store(T* __restrict__ out_u, const float2 (&acc)[Vec16<T>::N / 2]) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  const int lane = threadIdx.x & 31;
+  const int cl = lane % LPR;
   float r[VEC];
 #pragma unroll
   for (int i = 0; i < VEC / 2; ++i) { r[2 * i] = acc[i].x; r[2 * i + 1] = acc[i].y; }
@@ -536,7 +575,145 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
     float o[N_OUT];
 #pragma unroll
     for (int i = 0; i < N_OUT; ++i) o[i] = r[i];
-    store_vals<T, N_OUT>(out + u * D + cl * VEC + first, o);
+    store_vals<T, N_OUT>(out_u + cl * VEC + first, o);
+  }
+}
+
+// One unit (image b, in-image unit index uq = q * M + m) by the calling warp.
+template <typename T, int D, int MC, int U, bool FUSED, bool SR>
+__device__ __forceinline__ void
+msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
+              const int32_t* __restrict__ start, const T* __restrict__ loc,
+              const T* __restrict__ attn, T* __restrict__ out,
+              int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
+
+  const int MD = M * D;
+  const int lane = threadIdx.x & 31;
+  const int cl = lane % LPR;
+  const int LP = L * P;
+  const long long u = (long long)b * QM + uq;
+  const T* __restrict__ u_loc = loc + u * (LP * 2);
+  const T* __restrict__ u_att = attn + u * LP;
+  const T* __restrict__ vb = value + (long long)b * S * MD + (m * D + cl * VEC);
+
+  float2 acc[VEC / 2];
+#pragma unroll
+  for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+
+  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
+    SampleParams sp;
+    const bool have = base + lane < LP;
+    if constexpr (FUSED) {
+      int l;
+      float odx, ody;
+      sp = fused_params<T>(u_loc, u_att, ref + ((long long)b * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
+    } else {
+      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+    }
+    msda_fwd_gather_pass<T, D, U, SR>(vb, sp, have, MD, min(32, LP - base), acc);
+  }
+  msda_fwd_store<T, D>(out + u * D, acc);
+}
+
+// grid: x = units of one image (one warp each), y = image
+template <typename T, int D, int MC, int U, bool FUSED, bool SR>
+__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? MSDA_FWD_MIN_CTAS : (U == 2 ? 4 : 3))
+msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
+                   const int32_t* __restrict__ start, const T* __restrict__ loc,
+                   const T* __restrict__ attn, T* __restrict__ out,
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major) {
+  const int M = MC > 0 ? MC : Mrt;
+  int uq, m;  // unit inside image blockIdx.y, its head
+  if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
+  msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, (int)blockIdx.y, uq, m);
+}
+
+// PATCH-ORDERED forward for pixel-aligned queries (encoder self-attention: Lq == S, query i is pixel i of the pyramid
+// and samples around its own position).  A CTA owns one head of a PY x PX patch of queries of one level -- warp w walks
+// the PX queries of patch row w -- so the taps of neighbouring queries are served by this SM's L1 instead of each
+// going to L2 (unit-ordered kernel: 22 % L1 hit rate on the encoder shape, long-scoreboard stalls 63 %: profiles/).
+// Persistent CTAs pick work items (level patch, image, head) round-robin; levels are enumerated finest first, so
+// the big items come first and the static schedule ends balanced.  Pure scheduling: the arithmetic of a unit is
+// msda_fwd_unit, identical to the unit-ordered kernel, and every query in [0, Lq) is processed exactly once whatever
+// the level shapes are; if the queries are NOT pixel-aligned only locality is lost.  blockDim.x = 32 * PY.
+#ifndef MSDA_PATCH_MAX_THREADS
+#define MSDA_PATCH_MAX_THREADS 512
+#endif
+template <typename T, int D, int MC, bool FUSED, bool SR>
+__global__ void __launch_bounds__(MSDA_PATCH_MAX_THREADS, 2)
+msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
+                      const int32_t* __restrict__ start, const T* __restrict__ loc,
+                      const T* __restrict__ attn, T* __restrict__ out,
+                      int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int PX) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  const int M = MC > 0 ? MC : Mrt;
+  const int MD = M * D;
+  const int PY = blockDim.x >> 5;
+  const int w = threadIdx.x >> 5;
+  const int lane = threadIdx.x & 31;
+  const int cl = lane % LPR;
+  const int NM = N * M;
+  const int Lq = QM / M;
+  const int LP = L * P;
+  const bool have = lane < LP;
+  const LevelMeta lm = load_level_meta(shapes, start, lane, have, inv_p);  // of MY sample: the same for every unit
+  int total = 0, pixels = 0;  // patches / queries covered by the level grids
+  for (int l = 0; l < L; ++l) {
+    const int H = __ldg(shapes + 2 * l), W = __ldg(shapes + 2 * l + 1);
+    total += ((H + PY - 1) / PY) * ((W + PX - 1) / PX);
+    pixels += H * W;
+  }
+  const long long items = (long long)total * NM;
+  for (long long item = blockIdx.x; item < items; item += gridDim.x) {
+    const int bm = (int)(item % NM);
+    int patch = (int)(item / NM);
+    int l = 0, H = 0, W = 0, npx = 1, first = 0;  // first = index of the level's first query (queries are NOT tied to
+    for (; l < L; ++l) {                          // level_start_index, which describes `value`)
+      H = __ldg(shapes + 2 * l);
+      W = __ldg(shapes + 2 * l + 1);
+      npx = (W + PX - 1) / PX;
+      const int np = ((H + PY - 1) / PY) * npx;
+      if (patch < np) break;
+      patch -= np;
+      first += H * W;
+    }
+    const int y = (patch / npx) * PY + w;
+    const int x0 = (patch % npx) * PX;
+    if (y >= H) continue;  // warp-uniform: this patch row lies below the level
+    const int b = bm / M, m = bm % M;
+    const int q0 = first + y * W + x0;
+    const int x1 = min(PX, W - x0);
+    const int n_q = min(x1, Lq - q0);  // <= 0 when the level grids overshoot Lq
+    if (n_q <= 0) continue;
+    // walk the row: the loads of unit i + 1 are issued before the gathers of unit i (needs L * P <= 32: host-checked)
+    const T* __restrict__ vb = value + (long long)b * S * MD + (m * D + cl * VEC);
+    long long u = (long long)b * QM + (long long)q0 * M + m;
+    RawSample raw = load_raw<T, FUSED>(loc + u * (LP * 2), attn + u * LP, ref + ((long long)b * Lq + q0) * (L * RD), RD, lane, have, lm.l);
+    for (int i = 0; i < n_q; ++i) {
+      const RawSample cur = raw;
+      if (i + 1 < n_q) {
+        const long long un = u + M;
+        raw = load_raw<T, FUSED>(loc + un * (LP * 2), attn + un * LP, ref + ((long long)b * Lq + q0 + i + 1) * (L * RD), RD, lane, have, lm.l);
+      }
+      const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
+      float2 acc[VEC / 2];
+#pragma unroll
+      for (int k = 0; k < VEC / 2; ++k) acc[k] = make_float2(0.f, 0.f);
+      msda_fwd_gather_pass<T, D, 1, SR>(vb, sp, have, MD, LP, acc);
+      msda_fwd_store<T, D>(out + u * D, acc);
+      u += M;
+    }
+  }
+  // queries beyond the level grids (Lq > sum H*W: not pixel-aligned after all) in plain unit order
+  const long long tail = (long long)max(0, Lq - pixels) * NM;
+  for (long long t = (long long)blockIdx.x * PY + w; t < tail; t += (long long)gridDim.x * PY) {
+    const int bm = (int)(t % NM);
+    const int q = pixels + (int)(t / NM);
+    msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, bm / M, q * M + bm % M, bm % M);
   }
 }
 

@@ -133,6 +133,9 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
  *   "no_pdl"           0|1   launch the backward kernel without programmatic dependent launch
  *   "head_major"       0=auto, 1=unit-major CTAs, 2=head-major CTAs (one head x consecutive queries per CTA)
  *   "smem_records"     0=auto, 1=per-sample records broadcast with warp shuffles, 2=through shared memory (forward)
+ *   "patch_mode"       0=auto, 1=unit-ordered forward, 2=patch-ordered persistent forward (pixel-aligned queries)
+ *   "patch_px/py"      0=default, else patch width in queries / patch height (= warps per CTA, <= 16)
+ *   "patch_ctas"       0=auto, else persistent CTAs per SM of the patch-ordered forward
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

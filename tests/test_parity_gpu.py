@@ -22,7 +22,8 @@ pytestmark = pytest.mark.gpu
 @pytest.fixture(autouse=True)
 def _ops(cuda_device):
     msda.load_ops()
-    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records"):
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
+              "patch_py", "patch_ctas"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -128,7 +129,7 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 @pytest.mark.parametrize("no_pdl", [0, 1])
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
                                       ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2),
-                                      ("smem_records", 1), ("smem_records", 2)])
+                                      ("smem_records", 1), ("smem_records", 2), ("patch_mode", 2)])
 def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)
@@ -139,6 +140,28 @@ def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
     assert_close_grad_loc(got[2], want[2], x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
     assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
+
+
+@pytest.mark.parametrize("lq_delta", [0, 7, -5], ids=["Lq=S", "Lq>S", "Lq<S"])
+@pytest.mark.parametrize("px,py", [(8, 16), (8, 8), (3, 2), (16, 4)])
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16], ids=["f32", "bf16"])
+def test_patch_ordered_forward_is_the_same_function(lq_delta, px, py, dtype, cuda_device):
+    """The patch-ordered persistent forward (encoder scheduling) visits every query exactly once for any level shapes and
+    query count, and returns bit-identical results to the unit-ordered kernel (same per-unit arithmetic)."""
+    levels = ((13, 21), (7, 11), (4, 6), (2, 3))
+    S = sum(h * w for h, w in levels)
+    w = Workload("enc_small", 2, levels, S + lq_delta, M=8, P=4, D=32)
+    x = torch_inputs(w, seed=23, loc_mode="wide")
+    _capi.set_tuning("patch_mode", 1)
+    base = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    _capi.set_tuning("patch_mode", 2)
+    _capi.set_tuning("patch_px", px)
+    _capi.set_tuning("patch_py", py)
+    got = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    assert np.array_equal(got, base)
+    if dtype is None:
+        want = oracle64(x)[0]
+        assert_close(got, want, 1e-4, 1e-7 * rms(want), "out")
 
 
 # ---------------------------------------------------------------------------------------------------------

@@ -51,6 +51,7 @@ def main():
     ap.add_argument("--no-pdl", default="0")
     ap.add_argument("--head-major", default="1")
     ap.add_argument("--smem-records", default="0")
+    ap.add_argument("--patch", default="1:0:0:0", help="comma list of patch_mode:px:py:ctas")
     ap.add_argument("--tag", default="")
     ap.add_argument("--no-generic", action="store_true")
     ap.add_argument("--max-sets", type=int, default=24)
@@ -74,7 +75,9 @@ def main():
             sets = [device_inputs(w, seed=5 + i, device=dev, dtype=tdt, loc_mode=mode) for i in range(n_sets)]
             fwd = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
             bwd = lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
-            for sr, hm, var, u, wpb in itertools.product([int(x) for x in args.smem_records.split(",")], [int(x) for x in args.head_major.split(",")], [int(x) for x in args.no_pdl.split(",")], [int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+            for pm, sr, hm, var, u, wpb in itertools.product(args.patch.split(","), [int(x) for x in args.smem_records.split(",")], [int(x) for x in args.head_major.split(",")], [int(x) for x in args.no_pdl.split(",")], [int(x) for x in args.unrolls.split(",")], [int(x) for x in args.wpbs.split(",")]):
+                for k, v in zip(("patch_mode", "patch_px", "patch_py", "patch_ctas"), pm.split(":")):
+                    _capi.set_tuning(k, int(v))
                 _capi.set_tuning("smem_records", sr)
                 _capi.set_tuning("head_major", hm)
                 _capi.set_tuning("no_pdl", var)
@@ -83,7 +86,7 @@ def main():
                 _capi.set_tuning("bwd_unroll", u)
                 tf = time_graph(fwd, sets)
                 tb = time_graph(bwd, sets)
-                rec = dict(tag=args.tag, workload=name, dtype=args.dtype, loc=mode, sets=n_sets, no_pdl=var, head_major=hm, smem_records=sr, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
+                rec = dict(tag=args.tag, patch=pm, workload=name, dtype=args.dtype, loc=mode, sets=n_sets, no_pdl=var, head_major=hm, smem_records=sr, unroll=u, wpb=wpb, fwd_us=round(tf, 2), bwd_us=round(tb, 2),
                            fwd_frac=round(w.algorithmic_bytes(elt, False) / tf / 1e3 / peak, 4),
                            bwd_frac=round(w.algorithmic_bytes(elt, True) / tb / 1e3 / peak, 4),
                            fwd_gsps=round(w.samples / tf / 1e3, 3), bwd_gsps=round(w.samples / tb / 1e3, 3))
@@ -91,6 +94,7 @@ def main():
                 f.write(json.dumps(rec) + "\n")
             _capi.set_tuning("head_major", 0)
             _capi.set_tuning("smem_records", 0)
+            _capi.set_tuning("patch_mode", 0)
             if args.no_generic:
                 del sets
                 torch.cuda.empty_cache()
