@@ -88,6 +88,8 @@ def lib() -> ctypes.CDLL:
     L.msda_backward_workspace_bytes.argtypes = [dp, i]
     L.msda_backward.restype = i
     L.msda_backward.argtypes = [vp] * 10 + [sz, dp, i, i, vp]
+    L.msda_im2col_inference.restype = i
+    L.msda_im2col_inference.argtypes = [vp] * 6 + [i] * 7 + [vp, i]
     L.msda_fused_supported.restype = i
     L.msda_fused_supported.argtypes = [dp, i, i]
     L.msda_fused_forward.restype = i

@@ -538,6 +538,24 @@ int msda_forward_host(const void* value, const int32_t* spatial_shapes, const in
   return rc;
 }
 
+int msda_im2col_inference(void* stream, const void* data_value, const void* data_spatial_shapes,
+                          const void* data_level_start_index, const void* data_sampling_loc,
+                          const void* data_attn_weight, int batch_size, int spatial_size, int num_heads, int channels,
+                          int num_levels, int num_query, int num_point, void* data_col, int data_type) {
+  int dtype;
+  switch (data_type) {  // nvinfer1::DataType
+    case 0: dtype = MSDA_F32; break;
+    case 1: dtype = MSDA_F16; break;
+    default:
+      fail("msda_im2col_inference: unsupported nvinfer1::DataType %d (0 = kFLOAT, 1 = kHALF)", data_type);
+      return -1;
+  }
+  const msda_dims d = {batch_size, spatial_size, num_heads, channels, num_levels, num_query, num_point};
+  const int rc = msda_forward(data_value, (const int32_t*)data_spatial_shapes, (const int32_t*)data_level_start_index,
+                              data_sampling_loc, data_attn_weight, data_col, &d, dtype, stream);
+  return rc == 0 ? 0 : -1;
+}
+
 int msda_fused_supported(const msda_dims* dims, int dtype, int ref_dim) {
   if (!dims || elt_size(dtype) == 0) return 0;
   return fused_shape_ok(*dims, dtype, ref_dim) ? 1 : 0;

@@ -125,6 +125,26 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
                         const msda_dims* dims, int dtype, int flags, void* stream);
 
 /*
+ * TensorRT-plugin twin.  Same signature, argument order and return convention as the
+ * kernel wrapper the reference's `MsDeformIm2ColTRT` plugin calls from `IPluginV2IOExt::enqueue`
+ * (alonet/torch2trt/plugins/ms_deform_im2col/sources/ms_deform_im2col_kernel.h:10-26, ..._kernel.cu:261-327,
+ * called at ..._plugin.cpp:99-110): plugin inputs carry no batch dimension, `batch_size` comes from enqueue();
+ * `data_type` takes the values of nvinfer1::DataType (0 = kFLOAT, 1 = kHALF); anything else returns -1 like the
+ * reference; 0 = success.  All pointers are device memory, the launch goes on `stream`.
+ *   data_value (batch, spatial_size, num_heads, channels); data_sampling_loc (batch, num_query, num_heads, num_levels,
+ *   num_point, 2); data_attn_weight (batch, num_query, num_heads, num_levels, num_point);
+ *   data_col (batch, num_query, num_heads * channels).
+ * kHALF: storage is fp16, arithmetic fp32, and the pixel mapping is the operator's `loc * size - 0.5` -- the
+ * reference's half kernel maps `loc * (size - 1)` instead (..._kernel.cu:245-246, its `- 0.5` is commented out), which
+ * disagrees with its own float kernel and with `ms_deform_attn_core_pytorch`; the twin follows the float semantics.
+ * A maintainer swaps the call in `MsDeformIm2Col::enqueue` for this symbol.
+ */
+int msda_im2col_inference(void* stream, const void* data_value, const void* data_spatial_shapes,
+                          const void* data_level_start_index, const void* data_sampling_loc,
+                          const void* data_attn_weight, int batch_size, int spatial_size, int num_heads, int channels,
+                          int num_levels, int num_query, int num_point, void* data_col, int data_type);
+
+/*
  * Tuning knobs (benchmark / test use).  Unknown names return non-zero.  Names:
  *   "force_generic"    0|1   route every call through the shape-generic kernels
  *   "fwd_unroll"       0=auto, 1, 2 or 4 samples in flight per lane group in the vector forward kernel

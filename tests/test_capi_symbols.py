@@ -11,13 +11,14 @@ HEADER = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))
 def declared_functions():
     txt = open(HEADER).read()
     txt = re.sub(r"/\*.*?\*/", "", txt, flags=re.S)
-    return sorted(set(re.findall(r"\b(msda_[a-z_]+)\s*\(", txt)))
+    return sorted(set(re.findall(r"\b(msda_[a-z0-9_]+)\s*\(", txt)))
 
 
 def test_header_declares_the_expected_entry_points():
     names = declared_functions()
     for n in ("msda_forward", "msda_backward", "msda_backward_workspace_bytes", "msda_forward_host", "msda_version",
-              "msda_last_error_string", "msda_set_tuning", "msda_get_tuning", "msda_kernel_launch_count"):
+              "msda_last_error_string", "msda_set_tuning", "msda_get_tuning", "msda_kernel_launch_count",
+              "msda_im2col_inference", "msda_fused_forward", "msda_fused_backward", "msda_fused_supported"):
         assert n in names
 
 
@@ -46,13 +47,18 @@ def test_abi_version_and_error_channel():
     assert rc != 0 and "workspace too small" in _capi.last_error()
     assert lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.BF16) == 4 * 4 * 32
     assert lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.F32) == 0
+    # TensorRT-plugin twin: nvinfer1::DataType other than kFLOAT / kHALF -> -1 like the reference wrapper
+    assert lib.msda_im2col_inference(None, None, None, None, None, None, 1, 4, 1, 32, 1, 1, 1, None, 3) == -1
+    assert "unsupported nvinfer1::DataType" in _capi.last_error()
+    assert lib.msda_im2col_inference(None, None, None, None, None, None, 0, 4, 1, 32, 1, 1, 1, None, 0) == 0  # empty batch
     # empty problems succeed without touching the device
     dims = _capi.MsdaDims(0, 4, 1, 32, 1, 1, 1)
     assert lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), _capi.F32, None) == 0
 
 
 def test_tuning_knobs_roundtrip():
-    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major"):
+    for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records",
+              "patch_mode", "patch_px", "patch_py", "patch_ctas"):
         _capi.set_tuning(k, 3)
         assert _capi.get_tuning(k) == 3
         _capi.set_tuning(k, 0)
