@@ -59,6 +59,31 @@ int validate_dims(const msda_dims* d, int dtype) {
   return 0;
 }
 
+// cudaLaunchKernelEx with the programmatic-stream-serialization attribute (see pdl_wait / pdl_trigger in the kernels)
+template <typename... KArgs, typename... Args>
+cudaError_t launch_pdl(void (*kernel)(KArgs...), dim3 grid, dim3 block, size_t smem, cudaStream_t st, bool pdl, Args... args) {
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = grid;
+  cfg.blockDim = block;
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, KArgs(args)...);
+}
+
+int check_pdl_launch(cudaError_t e, const char* what) {
+  g_launches.fetch_add(1, std::memory_order_relaxed);
+  if (e != cudaSuccess) {
+    cudaGetLastError();
+    return fail("%s: CUDA launch failed: %s", what, cudaGetErrorString(e));
+  }
+  return 0;
+}
+
 bool aligned(const void* p, size_t a) { return (reinterpret_cast<uintptr_t>(p) % a) == 0; }
 
 struct Launch {
@@ -141,6 +166,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
+  const bool pdl = false;  // forward kernels launch normally (see pdl_wait / pdl_trigger in msda_kernels.cuh)
   // patch-ordered persistent kernel for pixel-aligned queries (knob "patch_mode": 0 = auto, 1 = off, 2 = on)
   const int pmk = g_patch_mode.load(std::memory_order_relaxed);
   if (d.num_levels * d.num_point <= 32 && (pmk == 2 || (pmk == 0 && patch_mode_auto(d)))) {  // one sample per lane
@@ -152,25 +178,27 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
     const int srk2 = g_smem_records.load(std::memory_order_relaxed);
     const bool sr2 = srk2 == 2 || (srk2 == 0 && sizeof(T) == 4);
     const dim3 grid((unsigned)(148 * ctas)), block((unsigned)(32 * py));
+    cudaError_t e;
 #define MSDA_FWDP(SR)                                                                                          \
-  msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR><<<grid, block, SR ? 24 * block.x : 0, st>>>(                \
-      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size,         \
-      d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px)
+  e = launch_pdl(msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR>, grid, block, SR ? 24 * block.x : 0, st, pdl,  \
+                 (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, \
+                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px)
     if (sr2) MSDA_FWDP(true); else MSDA_FWDP(false);
 #undef MSDA_FWDP
-    return check_launch(FUSED ? "msda_fused_forward(patch)" : "msda_forward(patch)");
+    return check_pdl_launch(e, FUSED ? "msda_fused_forward(patch)" : "msda_forward(patch)");
   }
   // records through shared memory (24 B / thread) or through shuffles: knob "smem_records" 0 = auto, 1 = shuffles, 2 = smem
   const int srk = g_smem_records.load(std::memory_order_relaxed);
   const bool sr = U == 1 && (srk == 2 || (srk == 0 && smem_records_auto(d, sizeof(T))));
+  cudaError_t e;
 #define MSDA_FWD(UU, SR)                                                                                      \
-  msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED, SR><<<l.grid, l.block, SR ? 24 * l.block.x : 0, st>>>(        \
-      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,     \
-      d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major)
+  e = launch_pdl(msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED, SR>, l.grid, l.block, SR ? 24 * l.block.x : 0, st, pdl, \
+                 (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,   \
+                 d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major)
   if (U == 1) { if (sr) MSDA_FWD(1, true); else MSDA_FWD(1, false); }
   else if (U == 2) MSDA_FWD(2, false); else MSDA_FWD(4, false);
 #undef MSDA_FWD
-  return check_launch(FUSED ? "msda_fused_forward" : "msda_forward(vector)");
+  return check_pdl_launch(e, FUSED ? "msda_fused_forward" : "msda_forward(vector)");
 }
 
 template <typename T>
@@ -220,8 +248,9 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   long long blocks = (n16 + 256 * 8 - 1) / (256 * 8);
   if (blocks < 1) blocks = 1;
   if (blocks > 148 * 4) blocks = 148 * 4;
-  msda::msda_zero_kernel<<<(unsigned)blocks, 256, 0, st>>>((uint4*)p, n16, (unsigned char*)p + n16 * 16, ntail);
-  return check_launch("msda_backward(zero grad_value)");
+  const cudaError_t e = launch_pdl(msda::msda_zero_kernel, dim3((unsigned)blocks), dim3(256), 0, st, false, (uint4*)p, n16,
+                                   (unsigned char*)p + n16 * 16, ntail);
+  return check_pdl_launch(e, "msda_backward(zero grad_value)");
 }
 
 template <typename T, int D, int MC, bool FUSED = false>

@@ -258,6 +258,17 @@ __device__ __forceinline__ void store_xy(__nv_bfloat16* p, float x, float y) {
 }
 __device__ __forceinline__ void store_xy(__half* p, float x, float y) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(x, y); }
 
+// Programmatic dependent launch (sm_90+).  A kernel launched with the "programmatic stream serialization" attribute may
+// become resident while its predecessor in the stream is still running; `pdl_wait` blocks until that predecessor has
+// completed and its writes are visible (no-op for a normal launch), `pdl_trigger` lets the NEXT kernel in the stream
+// start its launch early (only effective once every CTA of this grid has executed it or exited).  Used for ONE pair:
+// zero-fill (normal launch, triggers at once) -> backward kernel (gathers during the fill, waits before its first
+// scatter).  Chaining every kernel of a step this way (wait at the top, then trigger) was measured and rejected: the
+// fill can then only trigger after ITS wait, which serialises the backward launch behind it (C2 backward 13.0 -> 17.0 us),
+// and the forward gains nothing (5.35 -> 5.8 us): profiles/r1_sweep_rejected_pdl_chain.jsonl.
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;"); }
+
 // vectorised fp32 reduction into global memory (sm_90+): one 16-byte L2 atomic instead of four
 __device__ __forceinline__ void red_add_v4(float* addr, float a, float b, float c, float d) {
   asm volatile("red.global.add.v4.f32 [%0], {%1, %2, %3, %4};" ::"l"(addr), "f"(a), "f"(b), "f"(c), "f"(d) : "memory");
@@ -841,7 +852,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
       }
       // ---- scatter: needs the zero-fill of grad_value (previous kernel) complete and visible ----
       if (!fenced) {
-        asm volatile("griddepcontrol.wait;" ::: "memory");
+        pdl_wait();
         fenced = true;
       }
 #pragma unroll
@@ -1016,8 +1027,9 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
 // helpers: zero fill (128-bit stores, grid-stride) and fp32 -> 16-bit conversion of grad_value
 // ------------------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256) msda_zero_kernel(uint4* __restrict__ p, long long n16, unsigned char* __restrict__ tail, int ntail) {
-  // let a programmatically-dependent kernel (the backward gather pass) start while this fill is running
-  asm volatile("griddepcontrol.launch_dependents;");
+  // Launched NORMALLY (everything earlier in the stream is complete when it starts); releases the programmatically-
+  // dependent backward kernel at once, whose gather pass reads the op's inputs while this fill is running.
+  pdl_trigger();
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
