@@ -113,7 +113,7 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU implementation of the path (pure PyTorch), ported
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit"):
+def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit", warmup=1):
     """Times forward + autograd backward of oracle/msda_torch_port.py on the host cores.
 
     Returns (Gsamples/s, ms per step, steps run, sample description, threads)."""
@@ -138,6 +138,8 @@ def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit"):
                  grad_out=x["grad_out"][:, :lq].contiguous())
         desc = f"{workload.name}: N={w.N}, first {lq} of {workload.Lq} queries per image (bounded sample)"
     n = steps if steps is not None else max(3, min(200, int(budget_s / max(probe, 1e-4))))
+    for _ in range(max(0, warmup - 1)):  # the cost probe above was the first warm-up step
+        msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
     t0 = time.perf_counter()
     for _ in range(n):
         msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
@@ -152,12 +154,11 @@ def run_reference(args):
     from aloception_oss_b200.synthetic import WORKLOADS
 
     w = WORKLOADS[args.workload]
-    for _ in range(max(0, min(args.warmup, 2))):
-        pass
-    rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=120.0, steps=args.steps, loc_mode=args.loc_mode)
+    warm = max(3, min(args.warmup, 10))  # W >= 3 untimed steps (bounded: a CPU step takes ~20 ms)
+    rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=120.0, steps=args.steps, loc_mode=args.loc_mode, warmup=warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
-        "warmup": 1, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+        "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
         "config": {"workload": f"{w.name}: N={w.N}, levels={list(w.levels)}, Lq={w.Lq}, M={w.M}, P={w.P}, D={w.D}; "
                                "fwd + autograd bwd of the reference's pure-PyTorch CPU path (port)"},
@@ -165,14 +166,36 @@ def run_reference(args):
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ------------------------------------------------------------------------------------------------------------
 # own arm
 # ------------------------------------------------------------------------------------------------------------
+_JSON_FD = None
+
+
+def quiet_stdout():
+    """Keep stdout for the ONE JSON line: libraries (NCCL prints its version banner on fd 1) go to stderr."""
+    global _JSON_FD
+    if _JSON_FD is None:
+        sys.stdout.flush()
+        _JSON_FD = os.dup(1)
+        os.dup2(2, 1)
+
+
+def emit(line):
+    data = (json.dumps(line) + "\n").encode()
+    if _JSON_FD is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_JSON_FD, data)
+
+
 def main():
     args = parse_args()
+    quiet_stdout()
     if args.impl == "reference":
         return run_reference(args)
 
@@ -343,7 +366,7 @@ def main():
         }
         if extra:
             line["extra"] = extra
-        print(json.dumps(line), flush=True)
+        emit(line)
     if world > 1:
         dist.destroy_process_group()
 
