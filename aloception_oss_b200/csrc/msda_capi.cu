@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -152,6 +152,22 @@ bool patch_mode_auto(const msda_dims& d) {
   return false;
 }
 
+// forward: TMA-staged coarse levels (persistent CTAs, one per SM)?  knob "staged_mode": 0 = auto, 1 = off, 2 = on
+bool staged_mode_auto(const msda_dims& d) {
+  (void)d;
+  return false;
+}
+
+int sm_count() {
+  static int n = 0;
+  if (n == 0) {
+    int dev = 0, v = 0;
+    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
+    else n = 148;
+  }
+  return n;
+}
+
 int pick_unroll(int knob, int fallback) {
   const int u = knob;
   return (u == 1 || u == 2 || u == 4) ? u : fallback;
@@ -167,6 +183,42 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
   const bool pdl = false;  // forward kernels launch normally (see pdl_wait / pdl_trigger in msda_kernels.cuh)
+  // TMA-staged coarse levels, persistent CTAs, one per SM (knob "staged_mode")
+  const int smk = g_staged_mode.load(std::memory_order_relaxed);
+  if (d.num_levels * d.num_point <= 32 && (smk == 2 || (smk == 0 && staged_mode_auto(d)))) {
+    int warps = g_staged_warps.load(std::memory_order_relaxed);
+    if (warps <= 0 || warps > 32) warps = 32;
+    const int threads = 32 * warps;
+    const size_t rowb = (size_t)D * sizeof(T);
+    const size_t rec_bytes = ((size_t)threads * 24 + 127) & ~(size_t)127;
+    size_t tile_bytes = (size_t)(227 * 1024) - rec_bytes - rowb - 16;
+    const int kb = g_staged_kb.load(std::memory_order_relaxed);
+    if (kb > 0 && (size_t)kb * 1024 < tile_bytes) tile_bytes = (size_t)kb * 1024;
+    long long tile_rows = (long long)(tile_bytes / rowb);
+    if (tile_rows > d.spatial_size) tile_rows = d.spatial_size;
+    const size_t smem = rec_bytes + (size_t)tile_rows * rowb + rowb + 16;
+    const long long items = (long long)d.batch * d.num_heads * ((d.num_query + warps - 1) / warps);
+    if (items > 0x7fffffffLL) return fail("msda_forward(staged): too many work items");
+    long long ctas = (long long)sm_count();
+    if (ctas > items) ctas = items;
+    cudaError_t e;
+#define MSDA_FWDS(LPC)                                                                                                 \
+  do {                                                                                                                 \
+    auto kern = msda::msda_fwd_staged_kernel<T, D, MC, FUSED, 1024, 1, LPC>;                                           \
+    static std::atomic<size_t> smem_set{0}; /* per instantiation: raise the dynamic shared-memory limit when needed */ \
+    if (smem_set.load(std::memory_order_relaxed) < smem) {                                                             \
+      const cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
+      if (ae != cudaSuccess) return fail("msda_forward(staged): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(ae)); \
+      smem_set.store(smem, std::memory_order_relaxed);                                                                 \
+    }                                                                                                                  \
+    e = launch_pdl(kern, dim3((unsigned)ctas), dim3((unsigned)threads), smem, st, pdl, (const T*)value, shapes, start,  \
+                   (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, d.num_heads, d.num_levels,          \
+                   d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, (int)tile_rows);             \
+  } while (0)
+    if (d.num_levels * d.num_point == 16 && g_staged_variant.load(std::memory_order_relaxed) != 1) MSDA_FWDS(16); else MSDA_FWDS(0);
+#undef MSDA_FWDS
+    return check_pdl_launch(e, FUSED ? "msda_fused_forward(staged)" : "msda_forward(staged)");
+  }
   // patch-ordered persistent kernel for pixel-aligned queries (knob "patch_mode": 0 = auto, 1 = off, 2 = on)
   const int pmk = g_patch_mode.load(std::memory_order_relaxed);
   if (d.num_levels * d.num_point <= 32 && (pmk == 2 || (pmk == 0 && patch_mode_auto(d)))) {  // one sample per lane
@@ -222,10 +274,12 @@ int forward_typed(const void* value, const int32_t* shapes, const int32_t* start
     return d.num_heads == 8 ? launch_fwd_vec<T, DD, 8>(value, shapes, start, loc, attn, out, d, st)           \
                             : launch_fwd_vec<T, DD, 0>(value, shapes, start, loc, attn, out, d, st);
     switch (d.channels) {
+#ifndef MSDA_DEV_FAST
       MSDA_CASE(16)
-      MSDA_CASE(32)
       MSDA_CASE(64)
       MSDA_CASE(128)
+#endif
+      MSDA_CASE(32)
       default: break;
     }
 #undef MSDA_CASE
@@ -245,10 +299,34 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   const long long n16 = (long long)(bytes / 16);
   const int ntail = (int)(bytes % 16);
   // every CTA must be resident at once: the dependent backward kernel is released when all of them have started
-  long long blocks = (n16 + 256 * 8 - 1) / (256 * 8);
+  int zc = g_zero_ctas.load(std::memory_order_relaxed), zt = g_zero_threads.load(std::memory_order_relaxed);
+  // knob "zero_mode": 0 = auto, 1 = 128-bit store kernel, 2 = TMA bulk stores from a zeroed shared-memory buffer.
+  // Measured (profiles/r1_sweep_zero_fill.jsonl): the TMA fill loses 0.7-1.7 us on L2-sized fills that the backward
+  // kernel overlaps (C2 13.15 -> 13.9 us) and gains 2.5 % on HBM-sized ones (C4DEC, 728 MB: 291.6 -> 284.5 us).
+  const int zmode = g_zero_mode.load(std::memory_order_relaxed);
+  if (zmode == 2 || (zmode == 0 && bytes > ((size_t)256 << 20))) {
+    int ck = g_zero_chunk_kb.load(std::memory_order_relaxed);
+    if (ck <= 0 || ck > 200) ck = 32;
+    const int chunk = ck * 1024;
+    if (zc <= 0 || zc > 16) zc = 1;
+    long long blocks = ((long long)bytes + chunk - 1) / chunk;
+    if (blocks > 148LL * zc) blocks = 148LL * zc;
+    static std::atomic<int> smem_set{0};
+    if (smem_set.load(std::memory_order_relaxed) < chunk) {
+      const cudaError_t ae = cudaFuncSetAttribute(msda::msda_zero_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk);
+      if (ae != cudaSuccess) return fail("zero fill: cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+      smem_set.store(chunk, std::memory_order_relaxed);
+    }
+    const cudaError_t e = launch_pdl(msda::msda_zero_tma_kernel, dim3((unsigned)blocks), dim3(128), (size_t)chunk, st, false,
+                                     (unsigned char*)p, n16, ntail, chunk);
+    return check_pdl_launch(e, "msda_backward(zero grad_value, TMA)");
+  }
+  if (zc <= 0 || zc > 16) zc = 4;
+  if (zt <= 0 || zt > 256 || (zt & 31)) zt = 256;
+  long long blocks = (n16 + zt * 8 - 1) / (zt * 8);
   if (blocks < 1) blocks = 1;
-  if (blocks > 148 * 4) blocks = 148 * 4;
-  const cudaError_t e = launch_pdl(msda::msda_zero_kernel, dim3((unsigned)blocks), dim3(256), 0, st, false, (uint4*)p, n16,
+  if (blocks > 148LL * zc) blocks = 148LL * zc;
+  const cudaError_t e = launch_pdl(msda::msda_zero_kernel, dim3((unsigned)blocks), dim3((unsigned)zt), 0, st, false, (uint4*)p, n16,
                                    (unsigned char*)p + n16 * 16, ntail);
   return check_pdl_launch(e, "msda_backward(zero grad_value)");
 }
@@ -317,10 +395,12 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
              : launch_bwd_vec<T, DD, 0>(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, st); \
     break;
         switch (d.channels) {
+#ifndef MSDA_DEV_FAST
           MSDA_CASE(16)
-          MSDA_CASE(32)
           MSDA_CASE(64)
           MSDA_CASE(128)
+#endif
+          MSDA_CASE(32)
           default: break;
         }
 #undef MSDA_CASE
@@ -370,10 +450,12 @@ int fused_forward_typed(const void* value, const int32_t* shapes, const int32_t*
                ? launch_fwd_vec<T, DD, 8, true>(value, shapes, start, off, logits, out, d, st, ref, ref_dim)   \
                : launch_fwd_vec<T, DD, 0, true>(value, shapes, start, off, logits, out, d, st, ref, ref_dim);
   switch (d.channels) {
+#ifndef MSDA_DEV_FAST
     MSDA_CASE(16)
-    MSDA_CASE(32)
     MSDA_CASE(64)
     MSDA_CASE(128)
+#endif
+    MSDA_CASE(32)
     default: break;
   }
 #undef MSDA_CASE
@@ -400,10 +482,12 @@ int fused_backward_typed(const void* go, const void* value, const int32_t* shape
                                                            st, ref, ref_dim, gref);                                     \
     break;
   switch (d.channels) {
+#ifndef MSDA_DEV_FAST
     MSDA_CASE(16)
-    MSDA_CASE(32)
     MSDA_CASE(64)
     MSDA_CASE(128)
+#endif
+    MSDA_CASE(32)
     default: break;
   }
 #undef MSDA_CASE
@@ -442,6 +526,14 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "patch_px")) return &g_patch_px;
   if (!strcmp(name, "patch_py")) return &g_patch_py;
   if (!strcmp(name, "patch_ctas")) return &g_patch_ctas;
+  if (!strcmp(name, "zero_ctas")) return &g_zero_ctas;
+  if (!strcmp(name, "zero_mode")) return &g_zero_mode;
+  if (!strcmp(name, "zero_chunk_kb")) return &g_zero_chunk_kb;
+  if (!strcmp(name, "zero_threads")) return &g_zero_threads;
+  if (!strcmp(name, "staged_mode")) return &g_staged_mode;
+  if (!strcmp(name, "staged_kb")) return &g_staged_kb;
+  if (!strcmp(name, "staged_variant")) return &g_staged_variant;
+  if (!strcmp(name, "staged_warps")) return &g_staged_warps;
   return nullptr;
 }
 
@@ -475,8 +567,10 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case MSDA_F32: return forward_typed<float>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+#ifndef MSDA_DEV_FAST
     case MSDA_BF16: return forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
     case MSDA_F16: return forward_typed<__half>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
+#endif
     case MSDA_F64: return launch_fwd_generic<double>(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, d, units, st);
   }
   return fail("unreachable");
@@ -511,8 +605,10 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case MSDA_F32: return backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+#ifndef MSDA_DEV_FAST
     case MSDA_BF16: return backward_typed<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
     case MSDA_F16: return backward_typed<__half>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+#endif
     case MSDA_F64: return backward_typed<double>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
   }
   return fail("unreachable");
@@ -608,8 +704,10 @@ int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const i
   int rc = kUnsupported;
   switch (dtype) {
     case MSDA_F32: rc = fused_forward_typed<float>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
+#ifndef MSDA_DEV_FAST
     case MSDA_BF16: rc = fused_forward_typed<__nv_bfloat16>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
     case MSDA_F16: rc = fused_forward_typed<__half>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
+#endif
     default: break;
   }
   if (rc == kUnsupported) fail("msda_fused_forward: misaligned tensors");
@@ -644,8 +742,10 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
   int rc = kUnsupported;
   switch (dtype) {
     case MSDA_F32: rc = fused_backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
+#ifndef MSDA_DEV_FAST
     case MSDA_BF16: rc = fused_backward_typed<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
     case MSDA_F16: rc = fused_backward_typed<__half>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
+#endif
     default: break;
   }
   if (rc == kUnsupported) fail("msda_fused_backward: misaligned tensors");

@@ -729,6 +729,224 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
 }
 
 // ------------------------------------------------------------------------------------------------
+// STAGED FORWARD: the coarsest pyramid levels of one (image, head) live in shared memory, brought there by TMA
+// ------------------------------------------------------------------------------------------------
+// For calls with many queries per image (encoder self-attention: Lq = S) every (image, head) slab of the coarse levels
+// is gathered from thousands of times: with 4 levels and 4 points, HALF of all taps fall into the two coarsest
+// levels, which hold 6 % of the rows (794 rows x 128 B = 101 KB per head for the 100^2..13^2 pyramid, 169 KB for
+// 800x1333).  A persistent CTA (one per SM) owns a contiguous range of work items (image b, head m, 32 consecutive
+// queries); whenever (b, m) changes it stages the trailing levels that fit its tile -- rows [start[L0], S) of head m,
+// D*sizeof(T) bytes each, pitch M*D*sizeof(T) -- with one `cp.async.bulk` (TMA, 1-D bulk copy) per row, all
+// completing on one mbarrier.  Taps of staged levels are then LDS.128 from the tile (29-cycle latency, no L2 round
+// trip), the fine levels keep the LDG path.  Which levels are staged is decided IN the kernel (the level tensors are
+// device memory): the largest suffix of levels that is contiguous in `value` and fits `tile_rows`; nothing fits or
+// the levels are not laid out back to back -> L0 = L and the kernel degenerates to the plain gather.  Pure
+// scheduling/data placement: the arithmetic of a unit is the same as in msda_fwd_sg_kernel (bit-identical results).
+// Dynamic shared memory: [records 24 B/thread][tile_rows rows][one zero row][mbarrier].
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, int count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t done = 0;
+  const uint32_t a = smem_u32(bar);
+  while (!done)
+    asm volatile("{ .reg .pred p; mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2; selp.u32 %0, 1, 0, p; }"
+                 : "=r"(done) : "r"(a), "r"(parity) : "memory");
+}
+// TMA 1-D bulk copy global -> shared (bytes: multiple of 16; both addresses 16-byte aligned), completes on `bar`
+__device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+               ::"r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ uint4 lds128(const void* p) { return *reinterpret_cast<const uint4*>(p); }
+
+// TPB / MINB: launch bounds (1024 x 1: 64 registers, 32 warps per SM).  LPC: compile-time L*P (0 = run time) -- with
+// LPC = 16 the sample rounds are fully unrolled and the tail checks disappear.  Needs L*P <= 32 (one sample per lane:
+// the lane's level is fixed, so its metadata, tile / image offsets and row stride are loop invariants, the pointers
+// of a warp's consecutive units advance by constants, and the raw location / weight of the NEXT unit is fetched
+// before the gathers of the current one).
+__device__ __forceinline__ uint4 lds128_u32(uint32_t addr) {
+  uint4 r;
+  asm volatile("ld.shared.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "r"(addr));
+  return r;
+}
+
+template <typename T, int D, int MC, bool FUSED, int TPB, int MINB, int LPC>
+__global__ void __launch_bounds__(TPB, MINB)
+msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
+                       const int32_t* __restrict__ start, const T* __restrict__ loc,
+                       const T* __restrict__ attn, T* __restrict__ out,
+                       int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
+                       int tile_rows) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  constexpr int G = 32 / LPR;
+  constexpr int ES = (int)sizeof(T);
+  constexpr int ROWB = D * ES;
+  const int M = MC > 0 ? MC : Mrt;
+  const int MD = M * D;
+  const int nw = blockDim.x >> 5, w = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int g = lane / LPR, cl = lane % LPR;
+  const int Lq = QM / M;
+  const int LP = LPC > 0 ? LPC : L * P;
+
+  extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
+  uint4* rec_a = reinterpret_cast<uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);
+  float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
+  T* tile = reinterpret_cast<T*>(msda_dyn_smem + (((size_t)blockDim.x * 24 + 127) & ~(size_t)127));
+  T* zero_row = tile + (size_t)tile_rows * D;
+  uint64_t* bar = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(zero_row) + ROWB);
+
+  // the trailing levels [L0, L) that are stored back to back at the end of the image and fit the tile
+  int L0 = L, row0 = S;
+  for (int l = L - 1; l >= 0; --l) {
+    const int st = __ldg(start + l), hw = __ldg(shapes + 2 * l) * __ldg(shapes + 2 * l + 1);
+    if (st + hw != row0 || S - st > tile_rows) break;
+    L0 = l;
+    row0 = st;
+  }
+  const int staged_rows = S - row0;
+  const int s0 = L0 * P;  // samples >= s0 of a unit read the tile
+
+  if (threadIdx.x == 0) mbar_init(bar, 1);
+  for (int i = threadIdx.x; i < ROWB / 4; i += blockDim.x) reinterpret_cast<uint32_t*>(zero_row)[i] = 0u;
+  __syncthreads();
+
+  // ---- per-lane loop invariants: my sample's level ----
+  const bool have = lane < LP;
+  const LevelMeta lm = load_level_meta(shapes, start, lane, have, inv_p);
+  const bool mine_staged = lane >= s0;
+  const int rowmul = mine_staged ? D : MD;                                // elements per pixel step
+  const int lvl_off = mine_staged ? (lm.st - row0) * D : lm.st * MD;      // element offset of my level's first row
+  const int rs4 = (lm.W * rowmul) << 4;                                   // row stride, pre-shifted for the record
+  const uint32_t tile_s = smem_u32(tile) + (uint32_t)(cl * VEC * ES);
+  const int slane = have ? lane : 0;
+
+  const int nchunk = (Lq + nw - 1) / nw;  // work item = (image, head, nw consecutive queries: one per warp)
+  const int items = N * M * nchunk;       // < 2^31: host-checked
+  const int i0 = (int)((long long)items * blockIdx.x / gridDim.x), i1 = (int)((long long)items * (blockIdx.x + 1) / gridDim.x);
+  if (i0 >= i1) return;
+  int bm = i0 / nchunk, c = i0 % nchunk;  // the only divisions: items are walked incrementally
+  int cur_bm = -1;
+  uint32_t parity = 0;
+
+  // pointers of my warp's unit of item (bm, c); they advance by constants while the item stays in the same (image, head)
+  const T* p_loc; const T* p_att; const T* p_ref = nullptr; T* p_out;
+  auto seek = [&](int bm_, int c_) {
+    const int q = c_ * nw + w, b = bm_ / M, m = bm_ % M;
+    const long long u = (long long)b * QM + (long long)q * M + m;
+    p_loc = loc + (u * LP + slane) * 2;
+    p_att = attn + u * LP + slane;
+    p_out = out + u * D;
+    if constexpr (FUSED) p_ref = ref + (((long long)b * Lq + q) * L + lm.l) * RD;
+  };
+  const int d_att = nw * M * LP, d_out = nw * M * D, d_ref = nw * L * RD;
+  auto fetch = [&]() {
+    RawSample r;
+    load_xy(p_loc, r.x, r.y);
+    r.rx = r.ry = r.rw = r.rh = 0.f;
+    if constexpr (FUSED) {
+      r.a = have ? load_s(p_att) : -INFINITY;
+      r.rx = load_s(p_ref);
+      r.ry = load_s(p_ref + 1);
+      if (RD != 2) { r.rw = load_s(p_ref + 2); r.rh = load_s(p_ref + 3); }
+    } else {
+      r.a = load_s(p_att);
+    }
+    return r;
+  };
+  seek(bm, c);
+  RawSample raw;
+  raw.x = raw.y = raw.a = raw.rx = raw.ry = raw.rw = raw.rh = 0.f;
+  if (c * nw + w < Lq) raw = fetch();
+
+  for (int item = i0; item < i1; ++item) {
+    const int q = c * nw + w;
+    const int this_bm = bm;
+    const RawSample cur = raw;
+    T* const o_cur = p_out;
+    // advance to the next item and put its parameter loads in flight
+    if (++c == nchunk) { c = 0; ++bm; seek(bm, c); }
+    else { p_loc += 2 * d_att; p_att += d_att; p_out += d_out; if constexpr (FUSED) p_ref += d_ref; }
+    if (item + 1 < i1 && c * nw + w < Lq) raw = fetch();
+
+    if (this_bm != cur_bm) {  // CTA-uniform
+      cur_bm = this_bm;
+      if (staged_rows > 0) {
+        __syncthreads();  // every warp has finished reading the previous slab
+        if (threadIdx.x == 0) mbar_arrive_expect_tx(bar, (uint32_t)staged_rows * ROWB);
+        const T* src = value + ((long long)(this_bm / M) * S + row0) * MD + (this_bm % M) * D;
+        for (int r = threadIdx.x; r < staged_rows; r += blockDim.x)
+          tma_bulk_g2s(tile + (size_t)r * D, src + (long long)r * MD, ROWB, bar);
+        mbar_wait(bar, parity);
+        parity ^= 1u;
+      }
+    }
+    if (q >= Lq) continue;  // warp-uniform
+    const T* __restrict__ vb = value + (long long)(this_bm / M) * S * MD + ((this_bm % M) * D + cl * VEC);
+
+    const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
+    const Geo<float> ge = make_geo<float>(sp.lx, sp.ly, lm.H, lm.W, have);
+    const int off00 = lvl_off + ge.row00 * rowmul;
+    const int rsf = rs4 | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
+    const float a = sp.a;
+    __syncwarp();
+    rec_a[lane] = make_uint4((unsigned)off00, (unsigned)rsf, __float_as_uint(ge.hy * ge.hx * a), __float_as_uint(ge.hy * ge.lx * a));
+    rec_b[lane] = make_float2(ge.ly * ge.hx * a, ge.ly * ge.lx * a);
+    __syncwarp();
+
+    float2 acc[VEC / 2];
+#pragma unroll
+    for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+
+#pragma unroll
+    for (int k0 = 0; k0 < (LPC > 0 ? LPC : 32); k0 += G) {
+      if (LPC == 0 && k0 >= LP) break;
+      const int src = k0 + g;
+      const uint4 ra = rec_a[src];
+      const float2 rb = rec_b[src];
+      const int off = (int)ra.x;
+      int fl = (int)ra.y;
+      if ((LPC == 0 || LPC % G != 0) && src >= LP) fl = 0;
+      const float wt[4] = {__uint_as_float(ra.z), __uint_as_float(ra.w), rb.x, rb.y};
+      const bool all_ok = __all_sync(0xffffffffu, (fl & 15) == 15);
+      uint4 v[4];
+      if (all_ok && k0 >= s0) {  // whole round in the tile
+        const uint32_t a0 = tile_s + (uint32_t)off * ES;
+        const uint32_t a1 = a0 + (uint32_t)(fl >> 4) * ES;
+        v[0] = lds128_u32(a0); v[1] = lds128_u32(a0 + ROWB); v[2] = lds128_u32(a1); v[3] = lds128_u32(a1 + ROWB);
+      } else if (all_ok && k0 + G <= s0) {  // whole round in global memory
+        const T* t0 = vb + off;
+        const T* t1 = vb + (off + (fl >> 4));
+        v[0] = ldg128(t0); v[1] = ldg128(t0 + MD); v[2] = ldg128(t1); v[3] = ldg128(t1 + MD);
+      } else {  // mixed round or some tap invalid: generic loads (shared or global window), zero row for invalid taps
+        const bool stg = src >= s0;
+        const T* t0 = (stg ? tile + cl * VEC : vb) + off;
+        const T* t1 = t0 + (fl >> 4);
+        const int xs = stg ? D : MD;
+        const T* zp = zero_row;
+        const T* tp[4] = {(fl & 1) ? t0 : zp, (fl & 2) ? t0 + xs : zp, (fl & 4) ? t1 : zp, (fl & 8) ? t1 + xs : zp};
+#pragma unroll
+        for (int t = 0; t < 4; ++t) v[t] = *reinterpret_cast<const uint4*>(tp[t]);
+      }
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float f[VEC];
+        Vec16<T>::unpack(v[t], f);
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(wt[t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
+      }
+    }
+    msda_fwd_store<T, D>(o_cur, acc);
+  }
+}
+
+// ------------------------------------------------------------------------------------------------
 // VECTOR BACKWARD
 // ------------------------------------------------------------------------------------------------
 // grad_value accumulates in fp32 (`gv`): the caller's tensor for T=float, a workspace for 16-bit T.
@@ -1033,6 +1251,30 @@ __global__ void __launch_bounds__(256) msda_zero_kernel(uint4* __restrict__ p, l
   const long long stride = (long long)gridDim.x * blockDim.x;
   for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n16; i += stride) p[i] = make_uint4(0, 0, 0, 0);
   if (blockIdx.x == 0 && (int)threadIdx.x < ntail) tail[threadIdx.x] = 0;
+}
+
+// Zero fill through the TMA store path: each CTA clears one shared-memory buffer once and then ONE thread streams it
+// out with `cp.async.bulk.global.shared::cta` (bulk stores bypass the LSU store path and occupy one warp and no
+// registers worth mentioning, so the programmatically-dependent backward kernel gets the SMs to itself).
+// `chunk` bytes per bulk store (multiple of 16, <= the dynamic shared memory size); n16 = number of 16-byte pieces.
+__global__ void __launch_bounds__(128) msda_zero_tma_kernel(unsigned char* __restrict__ p, long long n16, int ntail, int chunk) {
+  extern __shared__ __align__(128) unsigned char zbuf[];
+  pdl_trigger();
+  for (int i = threadIdx.x; i < chunk / 16; i += blockDim.x) reinterpret_cast<uint4*>(zbuf)[i] = make_uint4(0, 0, 0, 0);
+  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  __syncthreads();
+  const long long bytes = n16 * 16;
+  if (threadIdx.x == 0) {
+    const uint32_t src = (uint32_t)__cvta_generic_to_shared(zbuf);
+    for (long long off = (long long)blockIdx.x * chunk; off < bytes; off += (long long)gridDim.x * chunk) {
+      const long long left = bytes - off;
+      const uint32_t n = (uint32_t)(left < chunk ? left : chunk);
+      asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(p + off), "r"(src), "r"(n) : "memory");
+    }
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+    asm volatile("cp.async.bulk.wait_group 0;" ::: "memory");
+  }
+  if (blockIdx.x == 0 && (int)threadIdx.x < ntail) p[bytes + threadIdx.x] = 0;
 }
 
 template <typename T>

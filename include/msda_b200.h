@@ -156,6 +156,12 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *   "patch_mode"       0=auto, 1=unit-ordered forward, 2=patch-ordered persistent forward (pixel-aligned queries)
  *   "patch_px/py"      0=default, else patch width in queries / patch height (= warps per CTA, <= 16)
  *   "patch_ctas"       0=auto, else persistent CTAs per SM of the patch-ordered forward
+ *   "staged_mode"      0=auto, 1=off, 2=TMA-staged persistent forward (coarse levels of one (image, head) in shared memory)
+ *   "staged_kb"        0=all the shared memory there is, else tile budget in KB;  "staged_warps" 0=32, else warps per CTA
+ *   "staged_variant"   0=sample rounds unrolled when L*P == 16, 1=run-time loop
+ *   "zero_mode"        0=auto, 1=128-bit store kernel, 2=TMA bulk-store kernel (zero fill of grad_value)
+ *   "zero_ctas"        0=default, else zero-fill CTAs per SM;  "zero_threads" threads per zero-fill CTA;
+ *   "zero_chunk_kb"    bytes per TMA bulk store of the zero fill, in KB
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

@@ -23,7 +23,8 @@ pytestmark = pytest.mark.gpu
 def _ops(cuda_device):
     msda.load_ops()
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
-              "patch_py", "patch_ctas"):
+              "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
+              "zero_threads", "zero_chunk_kb"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -129,7 +130,8 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 @pytest.mark.parametrize("no_pdl", [0, 1])
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
                                       ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2),
-                                      ("smem_records", 1), ("smem_records", 2), ("patch_mode", 2)])
+                                      ("smem_records", 1), ("smem_records", 2), ("patch_mode", 2),
+                                      ("staged_mode", 2), ("zero_mode", 2), ("zero_threads", 64)])
 def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)
@@ -162,6 +164,50 @@ def test_patch_ordered_forward_is_the_same_function(lq_delta, px, py, dtype, cud
     if dtype is None:
         want = oracle64(x)[0]
         assert_close(got, want, 1e-4, 1e-7 * rms(want), "out")
+
+
+@pytest.mark.parametrize("levels,lq,M,P", [
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 450, 8, 4),   # L*P = 16: unrolled instantiation; all but level 0 fit 4 KB
+    (((9, 11),), 333, 8, 4),                               # one level: the whole image is the tile (or nothing fits)
+    (((16, 16), (8, 8), (4, 4)), 500, 8, 3),               # ragged rounds (L*P = 9)
+    (((16, 16), (8, 8)), 100, 5, 4),                       # run-time head count
+    (((6, 5), (12, 10), (3, 2)), 200, 8, 4),               # levels not sorted by size: still a contiguous suffix
+])
+@pytest.mark.parametrize("kb", [0, 1, 4, 16])
+@pytest.mark.parametrize("variant,warps", [(0, 0), (1, 0), (0, 5)])
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16], ids=["f32", "bf16"])
+def test_tma_staged_forward_is_the_same_function(levels, lq, M, P, kb, variant, warps, dtype, cuda_device):
+    """The TMA-staged persistent forward (coarse levels of one (image, head) in shared memory) returns bit-identical
+    results to the unit-ordered kernel whatever part of the pyramid fits its tile (kb = tile budget; 0 = all it can get),
+    including out-of-range samples (zero row) and rounds that mix staged and unstaged levels."""
+    w = Workload("staged_small", 2, levels, lq, M=M, P=P, D=32)
+    x = torch_inputs(w, seed=29, loc_mode="wide")
+    _capi.set_tuning("staged_mode", 1)
+    base = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    _capi.set_tuning("staged_mode", 2)
+    _capi.set_tuning("staged_kb", kb)
+    _capi.set_tuning("staged_variant", variant)
+    _capi.set_tuning("staged_warps", warps)
+    n0 = _capi.kernel_launch_count()
+    got = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    assert _capi.kernel_launch_count() == n0 + 1
+    assert np.array_equal(got, base)
+    if dtype is None:
+        want = oracle64(x)[0]
+        assert_close(got, want, 1e-4, 1e-7 * rms(want), "out")
+
+
+def test_tma_staged_forward_full_size_encoder_call(cuda_device):
+    """Encoder shape (Lq = S = 13 294, N = 2): staged forward == unit-ordered forward, bit for bit."""
+    w = WORKLOADS["ENC"]
+    s = device_inputs(w, seed=41, device=cuda_device, loc_mode="raster")
+    f = lambda: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
+    _capi.set_tuning("staged_mode", 1)
+    base = f()
+    _capi.set_tuning("staged_mode", 2)
+    got = f()
+    torch.cuda.synchronize()
+    assert torch.equal(got, base)
 
 
 # ---------------------------------------------------------------------------------------------------------
