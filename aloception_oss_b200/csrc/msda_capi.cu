@@ -20,7 +20,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -183,6 +183,12 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
   const bool pdl = false;  // forward kernels launch normally (see pdl_wait / pdl_trigger in msda_kernels.cuh)
+  // speculative regular-window gather (knob "spec_mode": 0 = auto = on, 1 = off, 2 = on)
+  // Measured (profiles/r1_sweep_speculative_gather.jsonl): fp32 +3 % on decoder shapes, +11 % on encoder shapes; 16-bit +2..6 %
+  // except multi-wave decoder calls (C4DEC bf16: 47.5 -> 51.5 us, the clamped taps fetch real rows instead of the zero line).
+  const int spk = g_spec_mode.load(std::memory_order_relaxed);
+  const bool spec_auto = sizeof(T) == 4 || d.num_query >= 2048 || (long long)d.batch * d.num_query * d.num_heads <= 148LL * 36;
+  const int spec_on = spk == 1 ? 0 : (spk == 2 ? 1 : (spec_auto ? 1 : 0));
   // TMA-staged coarse levels, persistent CTAs, one per SM (knob "staged_mode")
   const int smk = g_staged_mode.load(std::memory_order_relaxed);
   if (d.num_levels * d.num_point <= 32 && (smk == 2 || (smk == 0 && staged_mode_auto(d)))) {
@@ -231,11 +237,13 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
     const bool sr2 = srk2 == 2 || (srk2 == 0 && sizeof(T) == 4);
     const dim3 grid((unsigned)(148 * ctas)), block((unsigned)(32 * py));
     cudaError_t e;
-#define MSDA_FWDP(SR)                                                                                          \
-  e = launch_pdl(msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR>, grid, block, SR ? 24 * block.x : 0, st, pdl,  \
+#define MSDA_FWDP(SR, MINB)                                                                                    \
+  e = launch_pdl(msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR, MINB>, grid, block, SR ? 24 * block.x : 0, st, pdl,  \
                  (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, \
-                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px)
-    if (sr2) MSDA_FWDP(true); else MSDA_FWDP(false);
+                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px, spec_on)
+    const bool lean = 32 * py * ctas > 1024;  // more than 32 warps per SM: the 40-register instantiation
+    if (sr2) { if (lean) MSDA_FWDP(true, 3); else MSDA_FWDP(true, 2); }
+    else { if (lean) MSDA_FWDP(false, 3); else MSDA_FWDP(false, 2); }
 #undef MSDA_FWDP
     return check_pdl_launch(e, FUSED ? "msda_fused_forward(patch)" : "msda_forward(patch)");
   }
@@ -246,7 +254,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
 #define MSDA_FWD(UU, SR)                                                                                      \
   e = launch_pdl(msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED, SR>, l.grid, l.block, SR ? 24 * l.block.x : 0, st, pdl, \
                  (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,   \
-                 d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major)
+                 d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, l.head_major, spec_on)
   if (U == 1) { if (sr) MSDA_FWD(1, true); else MSDA_FWD(1, false); }
   else if (U == 2) MSDA_FWD(2, false); else MSDA_FWD(4, false);
 #undef MSDA_FWD
@@ -527,6 +535,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "patch_py")) return &g_patch_py;
   if (!strcmp(name, "patch_ctas")) return &g_patch_ctas;
   if (!strcmp(name, "zero_ctas")) return &g_zero_ctas;
+  if (!strcmp(name, "spec_mode")) return &g_spec_mode;
   if (!strcmp(name, "zero_mode")) return &g_zero_mode;
   if (!strcmp(name, "zero_chunk_kb")) return &g_zero_chunk_kb;
   if (!strcmp(name, "zero_threads")) return &g_zero_threads;

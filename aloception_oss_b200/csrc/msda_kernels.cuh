@@ -488,7 +488,16 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // the same L1 data pipe the tap rows return through).  Dynamic shared memory: 24 bytes per thread.
 // Gather + reduce + store of one pass (<= 32 samples, one per lane) of one unit, given the lane's sample parameters.
 // `acc` carries the partial sums across passes.
-template <typename T, int D, int U, bool SR>
+// SPEC ("speculative regular window"): the sample's lane moves the 2x2 tap window fully inside the level (needs H, W >= 2) and
+// gives the taps that fell outside a ZERO WEIGHT instead of a zero address: x0 = -1 -> window columns (0, 1) with weights
+// (lx, 0); x0 = W-1 -> columns (W-2, W-1) with weights (0, hx); same for rows; a sample outside the (-1, size) window gets
+// four zero weights on the level's first pixels.  Every tap address is then valid and regular (base, +MD, +stride,
+// +stride+MD), so the rounds need no validity flags, no vote and no pointer selects (the flagged path costs ~30 extra
+// instructions on every round that holds ONE invalid tap: 48 % of the rounds of an encoder call with +-4 pixel offsets,
+// 83 % of its 13x13-level rounds).  The effective (non-zero-weight) FMAs are the same, in the same order, with the same
+// weights: results are bit-identical as long as every loaded value is finite; 0 * Inf / 0 * NaN from a clamped tap would
+// differ, so the caller checks the unit's sums and redoes a non-finite unit on the flagged path (msda_fwd_unit).
+template <typename T, int D, int U, bool SR, bool SPEC = false>
 __device__ __forceinline__ void
 msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have, int MD, int cnt, float2 (&acc)[Vec16<T>::N / 2]) {
   constexpr int VEC = Vec16<T>::N;
@@ -499,6 +508,74 @@ msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have
   extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
   uint4* rec_a = reinterpret_cast<uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);  // this warp's 32 records
   float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
+
+  if constexpr (SPEC) {
+    const float fH = (float)sp.H, fW = (float)sp.W;
+    const float y = fma(sp.ly, fH, -0.5f), x = fma(sp.lx, fW, -0.5f);  // same roundings as make_geo
+    const bool inside = have && y > -1.f && x > -1.f && y < fH && x < fW;
+    const float fy = floorf(y), fx = floorf(x);
+    int y0 = (int)fy, x0 = (int)fx;
+    const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+    float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
+    if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > sp.H - 2) { y0 = sp.H - 2; wy1 = hy; wy0 = 0.f; }
+    if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > sp.W - 2) { x0 = sp.W - 2; wx1 = hx; wx0 = 0.f; }
+    if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; }
+    const float a = sp.a;
+    const float w00 = wy0 * wx0 * a, w01 = wy0 * wx1 * a, w10 = wy1 * wx0 * a, w11 = wy1 * wx1 * a;
+    // BYTE offsets from the unit's base pointer (32-bit: the host checks S*M*D*sizeof(T) <= 2^29): a tap pointer is then
+    // one 64-bit add instead of an index add + scale + carry chain
+    const unsigned off00 = (unsigned)((sp.st + y0 * sp.W + x0) * MD) * (unsigned)sizeof(T);
+    const unsigned stride = (unsigned)(sp.W * MD) * (unsigned)sizeof(T);
+    if constexpr (SR) {
+      __syncwarp();
+      rec_a[lane] = make_uint4(off00, stride, __float_as_uint(w00), __float_as_uint(w01));
+      rec_b[lane] = make_float2(w10, w11);
+      __syncwarp();
+    }
+    const char* vbc = reinterpret_cast<const char*>(vb);
+    const size_t mdb = (size_t)MD * sizeof(T);
+    auto round = [&](int k0) {
+      unsigned off[U], rs[U];
+      float w[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const int src = k0 + j * G + g;  // < 32
+        if constexpr (SR) {
+          const uint4 ra = rec_a[src];
+          const float2 rb = rec_b[src];
+          off[j] = ra.x; rs[j] = ra.y;
+          w[j][0] = __uint_as_float(ra.z); w[j][1] = __uint_as_float(ra.w); w[j][2] = rb.x; w[j][3] = rb.y;
+        } else {
+          off[j] = __shfl_sync(0xffffffffu, off00, src);
+          rs[j] = __shfl_sync(0xffffffffu, stride, src);
+          w[j][0] = __shfl_sync(0xffffffffu, w00, src);
+          w[j][1] = __shfl_sync(0xffffffffu, w01, src);
+          w[j][2] = __shfl_sync(0xffffffffu, w10, src);
+          w[j][3] = __shfl_sync(0xffffffffu, w11, src);
+        }
+      }
+      uint4 v[U][4];
+#pragma unroll
+      for (int j = 0; j < U; ++j) {
+        const char* t0 = vbc + off[j];
+        const char* t1 = t0 + rs[j];
+        v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + mdb); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + mdb);
+      }
+#pragma unroll
+      for (int j = 0; j < U; ++j)
+#pragma unroll
+        for (int t = 0; t < 4; ++t) {
+          float f[VEC];
+          Vec16<T>::unpack(v[j][t], f);
+#pragma unroll
+          for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
+        }
+    };
+    // (a fully unrolled 4-round variant for L*P = 16 was measured 5 % SLOWER -- 100.1 vs 94.8 us on the encoder shape: the
+    // kernel grows by 70 instructions and ptxas needs 2 spill slots at 40 registers)
+    for (int k0 = 0; k0 < cnt; k0 += G * U) round(k0);  // warp-uniform trip count; lanes >= cnt hold zero-weight records
+    return;
+  }
 
   SampleGeo sg;
   Geo<float> ge;
@@ -568,26 +645,36 @@ msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have
   }
 }
 
-// sum the lane groups' partial sums and write the unit's D outputs
+// sum the lane groups' partial sums (scattered over the warp: GroupReduceScatter) ...
+template <typename T, int D>
+__device__ __forceinline__ void msda_fwd_reduce(const float2 (&acc)[Vec16<T>::N / 2], float (&o)[GroupReduceScatter<Vec16<T>::N, D / Vec16<T>::N>::N_OUT],
+                                                int& first, bool& owner) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  const int lane = threadIdx.x & 31;
+  float r[VEC];
+#pragma unroll
+  for (int i = 0; i < VEC / 2; ++i) { r[2 * i] = acc[i].x; r[2 * i + 1] = acc[i].y; }
+  first = 0;
+  owner = true;
+  reduce_scatter_steps<VEC, LPR, LPR>(r, lane, first, owner);
+  constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
+#pragma unroll
+  for (int i = 0; i < N_OUT; ++i) o[i] = r[i];
+}
+
+// ... and write the unit's D outputs
 template <typename T, int D>
 __device__ __forceinline__ void msda_fwd_store(T* __restrict__ out_u, const float2 (&acc)[Vec16<T>::N / 2]) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
-  const int lane = threadIdx.x & 31;
-  const int cl = lane % LPR;
-  float r[VEC];
-#pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) { r[2 * i] = acc[i].x; r[2 * i + 1] = acc[i].y; }
-  int first = 0;
-  bool owner = true;
-  reduce_scatter_steps<VEC, LPR, LPR>(r, lane, first, owner);
   constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
-  if (owner) {
-    float o[N_OUT];
-#pragma unroll
-    for (int i = 0; i < N_OUT; ++i) o[i] = r[i];
-    store_vals<T, N_OUT>(out_u + cl * VEC + first, o);
-  }
+  const int cl = (threadIdx.x & 31) % LPR;
+  float o[N_OUT];
+  int first;
+  bool owner;
+  msda_fwd_reduce<T, D>(acc, o, first, owner);
+  if (owner) store_vals<T, N_OUT>(out_u + cl * VEC + first, o);
 }
 
 // One unit (image b, in-image unit index uq = q * M + m) by the calling warp.
@@ -596,7 +683,8 @@ __device__ __forceinline__ void
 msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
               const int32_t* __restrict__ start, const T* __restrict__ loc,
               const T* __restrict__ attn, T* __restrict__ out,
-              int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m) {
+              int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m,
+              int spec_on = 0) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
@@ -610,23 +698,58 @@ msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
   const T* __restrict__ u_att = attn + u * LP;
   const T* __restrict__ vb = value + (long long)b * S * MD + (m * D + cl * VEC);
 
+  constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
   float2 acc[VEC / 2];
+  float o[N_OUT];
+  int first;
+  bool owner;
+  bool spec = spec_on != 0;  // try the speculative regular-window gather first (see msda_fwd_gather_pass)
+  for (;;) {
 #pragma unroll
-  for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
-
-  for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
-    SampleParams sp;
-    const bool have = base + lane < LP;
-    if constexpr (FUSED) {
-      int l;
-      float odx, ody;
-      sp = fused_params<T>(u_loc, u_att, ref + ((long long)b * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
-    } else {
-      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+    for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    bool restart = false;
+    for (int base = 0; base < LP; base += 32) {  // 32 samples per pass, one per lane (FUSED: L*P <= 32, one pass)
+      SampleParams sp;
+      const bool have = base + lane < LP;
+      if constexpr (FUSED) {
+        int l;
+        float odx, ody;
+        sp = fused_params<T>(u_loc, u_att, ref + ((long long)b * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
+      } else {
+        sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+      }
+      // the regular window needs levels of at least 2 x 2 pixels (warp-uniform; the decision sticks for the unit)
+      if (spec && !__all_sync(0xffffffffu, !have || (sp.H >= 2 && sp.W >= 2))) {
+        spec = false;
+        if (base > 0) { restart = true; break; }  // earlier passes were speculative: redo the unit on the flagged path
+      }
+      if (spec) msda_fwd_gather_pass<T, D, U, SR, true>(vb, sp, have, MD, min(32, LP - base), acc);
+      else msda_fwd_gather_pass<T, D, U, SR, false>(vb, sp, have, MD, min(32, LP - base), acc);
     }
-    msda_fwd_gather_pass<T, D, U, SR>(vb, sp, have, MD, min(32, LP - base), acc);
+    if (restart) continue;
+    msda_fwd_reduce<T, D>(acc, o, first, owner);
+    if (spec) {
+      bool bad = false;
+#pragma unroll
+      for (int i = 0; i < N_OUT; ++i) bad = bad || !(fabsf(o[i]) <= 3.402823466e38f);
+      if (__any_sync(0xffffffffu, bad)) {  // a non-finite value met a zero weight (or is simply there): the flagged path decides
+        spec = false;
+        continue;
+      }
+    }
+    break;
   }
-  msda_fwd_store<T, D>(out + u * D, acc);
+  if (owner) store_vals<T, N_OUT>(out + u * D + cl * VEC + first, o);
+}
+
+// The flagged (exact zero-line) path of one unit as an out-of-line call: the persistent kernels take it only for units whose
+// speculative sums came out non-finite or when a level is narrower than 2 pixels, and must not pay its registers.
+template <typename T, int D, int MC, bool FUSED, bool SR>
+__device__ __noinline__ void
+msda_fwd_unit_flagged(const T* __restrict__ value, const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                      const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
+                      int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m) {
+  msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b, uq, m, 0);
 }
 
 // grid: x = units of one image (one warp each), y = image
@@ -635,11 +758,11 @@ __global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? MSDA_FWD_MIN_CTAS :
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major, int spec_on) {
   const int M = MC > 0 ? MC : Mrt;
   int uq, m;  // unit inside image blockIdx.y, its head
   if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
-  msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, (int)blockIdx.y, uq, m);
+  msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, (int)blockIdx.y, uq, m, spec_on);
 }
 
 // PATCH-ORDERED forward for pixel-aligned queries (encoder self-attention: Lq == S, query i is pixel i of the pyramid
@@ -653,12 +776,12 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
 #ifndef MSDA_PATCH_MAX_THREADS
 #define MSDA_PATCH_MAX_THREADS 512
 #endif
-template <typename T, int D, int MC, bool FUSED, bool SR>
-__global__ void __launch_bounds__(MSDA_PATCH_MAX_THREADS, 2)
+template <typename T, int D, int MC, bool FUSED, bool SR, int MINB = 2>
+__global__ void __launch_bounds__(MSDA_PATCH_MAX_THREADS, MINB)
 msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                       const int32_t* __restrict__ start, const T* __restrict__ loc,
                       const T* __restrict__ attn, T* __restrict__ out,
-                      int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int PX) {
+                      int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int PX, int spec_on) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   const int M = MC > 0 ? MC : Mrt;
@@ -672,6 +795,7 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
   const int LP = L * P;
   const bool have = lane < LP;
   const LevelMeta lm = load_level_meta(shapes, start, lane, have, inv_p);  // of MY sample: the same for every unit
+  const bool spec_ok = spec_on != 0 && __all_sync(0xffffffffu, !have || (lm.H >= 2 && lm.W >= 2));
   int total = 0, pixels = 0;  // patches / queries covered by the level grids
   for (int l = 0; l < L; ++l) {
     const int H = __ldg(shapes + 2 * l), W = __ldg(shapes + 2 * l + 1);
@@ -711,11 +835,26 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
         raw = load_raw<T, FUSED>(loc + un * (LP * 2), attn + un * LP, ref + ((long long)b * Lq + q0 + i + 1) * (L * RD), RD, lane, have, lm.l);
       }
       const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
+      constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
       float2 acc[VEC / 2];
+      float o[N_OUT];
+      int first;
+      bool owner;
+      bool done = false;
+      if (spec_ok) {  // speculative regular-window gather (msda_fwd_gather_pass); a non-finite sum sends the unit to the flagged path
 #pragma unroll
-      for (int k = 0; k < VEC / 2; ++k) acc[k] = make_float2(0.f, 0.f);
-      msda_fwd_gather_pass<T, D, 1, SR>(vb, sp, have, MD, LP, acc);
-      msda_fwd_store<T, D>(out + u * D, acc);
+        for (int k = 0; k < VEC / 2; ++k) acc[k] = make_float2(0.f, 0.f);
+        msda_fwd_gather_pass<T, D, 1, SR, true>(vb, sp, have, MD, LP, acc);
+        msda_fwd_reduce<T, D>(acc, o, first, owner);
+        bool bad = false;
+#pragma unroll
+        for (int k = 0; k < N_OUT; ++k) bad = bad || !(fabsf(o[k]) <= 3.402823466e38f);
+        done = !__any_sync(0xffffffffu, bad);
+        if (done && owner) store_vals<T, N_OUT>(out + u * D + cl * VEC + first, o);
+      }
+      if (!done)
+        msda_fwd_unit_flagged<T, D, MC, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b,
+                                                   (int)(u - (long long)b * QM), m);
       u += M;
     }
   }
@@ -724,7 +863,7 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
   for (long long t = (long long)blockIdx.x * PY + w; t < tail; t += (long long)gridDim.x * PY) {
     const int bm = (int)(t % NM);
     const int q = pixels + (int)(t / NM);
-    msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, bm / M, q * M + bm % M, bm % M);
+    msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, bm / M, q * M + bm % M, bm % M, spec_on);
   }
 }
 

@@ -159,6 +159,8 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *   "staged_mode"      0=auto, 1=off, 2=TMA-staged persistent forward (coarse levels of one (image, head) in shared memory)
  *   "staged_kb"        0=all the shared memory there is, else tile budget in KB;  "staged_warps" 0=32, else warps per CTA
  *   "staged_variant"   0=sample rounds unrolled when L*P == 16, 1=run-time loop
+ *   "spec_mode"        0=auto (on), 1=flagged forward gather (zero-line address for invalid taps), 2=speculative regular-window
+ *                      gather (zero weight on a clamped address; non-finite sums are redone on the flagged path)
  *   "zero_mode"        0=auto, 1=128-bit store kernel, 2=TMA bulk-store kernel (zero fill of grad_value)
  *   "zero_ctas"        0=default, else zero-fill CTAs per SM;  "zero_threads" threads per zero-fill CTA;
  *   "zero_chunk_kb"    bytes per TMA bulk store of the zero fill, in KB

@@ -24,7 +24,7 @@ def _ops(cuda_device):
     msda.load_ops()
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
               "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
-              "zero_threads", "zero_chunk_kb"):
+              "zero_threads", "zero_chunk_kb", "spec_mode"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -131,7 +131,7 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
                                       ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2),
                                       ("smem_records", 1), ("smem_records", 2), ("patch_mode", 2),
-                                      ("staged_mode", 2), ("zero_mode", 2), ("zero_threads", 64)])
+                                      ("staged_mode", 2), ("zero_mode", 2), ("zero_threads", 64), ("spec_mode", 1)])
 def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)
@@ -164,6 +164,37 @@ def test_patch_ordered_forward_is_the_same_function(lq_delta, px, py, dtype, cud
     if dtype is None:
         want = oracle64(x)[0]
         assert_close(got, want, 1e-4, 1e-7 * rms(want), "out")
+
+
+@pytest.mark.parametrize("levels,lq,M,P", [
+    (((20, 27), (10, 14), (5, 7), (3, 4)), 700, 8, 4),    # out-of-range samples on every level
+    (((9, 1), (1, 7), (2, 2), (1, 1)), 300, 8, 4),         # levels narrower than 2 pixels: the flagged path must take over
+    (((16, 16), (8, 8), (2, 3)), 200, 8, 17),              # L*P = 51: two passes
+    (((2, 2), (16, 16), (1, 9)), 150, 8, 12),              # L*P = 36: the degenerate level only shows up in the second pass
+    (((16, 16), (8, 8)), 100, 5, 4),                       # run-time head count
+])
+@pytest.mark.parametrize("poison", [None, float("nan"), float("inf")], ids=["finite", "nan", "inf"])
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16, torch.float16], ids=["f32", "bf16", "f16"])
+@pytest.mark.parametrize("patch", [1, 2], ids=["unit-ordered", "patch-ordered"])
+def test_speculative_gather_is_the_same_function(levels, lq, M, P, poison, dtype, patch, cuda_device):
+    """The speculative regular-window forward gather (taps outside a level get a zero WEIGHT on a clamped in-range address
+    instead of a zero-line ADDRESS) returns bit-identical results to the flagged path -- also when value holds NaN / Inf next
+    to out-of-range samples (0 * Inf would differ: such units are detected by their non-finite sums and redone)."""
+    if patch == 2 and P * len(levels) > 32:
+        pytest.skip("patch-ordered kernel needs L*P <= 32")
+    w = Workload("spec_small", 2, levels, lq, M=M, P=P, D=32)
+    x = torch_inputs(w, seed=31, loc_mode="wide")
+    if poison is not None:
+        x["value"][:, ::29] = poison  # sparse: about half of the units stay finite, and clamped zero-weight taps do hit poisoned pixels
+    _capi.set_tuning("patch_mode", 1)
+    _capi.set_tuning("spec_mode", 1)
+    base = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    _capi.set_tuning("patch_mode", patch)
+    _capi.set_tuning("spec_mode", 2)
+    got = run_op(x, cuda_device, dtype=dtype, need_grad=False)[0]
+    assert np.array_equal(got, base, equal_nan=True)
+    if poison is not None and lq >= 300:
+        assert np.isfinite(base).any() and not np.isfinite(base).all()
 
 
 @pytest.mark.parametrize("levels,lq,M,P", [
