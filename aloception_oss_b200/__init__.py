@@ -18,6 +18,7 @@ from .functions import (  # noqa: F401
     ms_deform_attn_forward,
 )
 from .modules import MSDeformAttn  # noqa: F401
+from . import transformer  # noqa: F401  (encoder / decoder layer loop around the operator)
 
 __all__ = [
     "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "load_MultiScaleDeformableAttention", "load_ops",

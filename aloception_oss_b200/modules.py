@@ -100,6 +100,11 @@ class MSDeformAttn(nn.Module):
         if reference_points.shape[-1] not in (2, 4):
             raise ValueError(
                 "Last dim of reference_points must be 2 or 4, but get {} instead.".format(reference_points.shape[-1]))
+        if reference_points.dtype != value.dtype and "is_tracing" not in kwargs:
+            # mixed precision (torch.autocast runs the Linear layers in bf16/fp16 while the reference points stay fp32): the
+            # operator takes ONE storage dtype -- value's -- and does its arithmetic in fp32 regardless
+            reference_points = reference_points.to(value.dtype)
+            offsets, weights = offsets.to(value.dtype), weights.to(value.dtype)
         if self.fused and "is_tracing" not in kwargs and fused_supported(value, input_spatial_shapes, reference_points,
                                                                         offsets, weights):
             output = MSDeformAttnFusedFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
@@ -120,5 +125,6 @@ class MSDeformAttn(nn.Module):
             output = ms_deform_attn_core_pytorch(value, input_spatial_shapes, locations, weights)
         else:
             output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
-                                                locations.contiguous(), weights.contiguous(), self.im2col_step)
+                                                locations.to(value.dtype).contiguous(), weights.to(value.dtype).contiguous(),
+                                                self.im2col_step)
         return self.output_proj(output)

@@ -44,6 +44,7 @@ def parse_args():
     ap.add_argument("--loc-mode", default="unit")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU's NUMA-local CPUs")
     ap.add_argument("--extra", action="store_true", help="also time the other COCO shapes (reported under 'extra')")
     return ap.parse_args()
 
@@ -193,6 +194,22 @@ def emit(line):
         os.write(_JSON_FD, data)
 
 
+def bind_near_gpu(index):
+    """Pin this process to the CPUs NVML reports as local to GPU `index` (NUMA node of its PCIe root), BEFORE any pinned
+    host buffer is allocated, so that the e2e staging memory is first-touched next to the GPU.  Returns a short note."""
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        before = len(os.sched_getaffinity(0))
+        pynvml.nvmlDeviceSetCpuAffinity(h)
+        after = len(os.sched_getaffinity(0))
+        return f"cpu affinity {before} -> {after} cpus (nvmlDeviceSetCpuAffinity)"
+    except Exception as e:  # no NUMA information in this VM, or not permitted: run unpinned
+        return f"unpinned ({type(e).__name__})"
+
+
 def main():
     args = parse_args()
     quiet_stdout()
@@ -210,6 +227,8 @@ def main():
     rank = int(os.environ.get("RANK", "0"))
     local = int(os.environ.get("LOCAL_RANK", "0"))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
+    all_cpus = os.sched_getaffinity(0)
+    numa_note = bind_near_gpu(local) if not args.no_bind else "unpinned (--no-bind)"
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
     if world > 1:
@@ -339,6 +358,7 @@ def main():
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
+        os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
         rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=12.0, loc_mode=args.loc_mode)
         cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
                     "sample": f"{desc}; {n} steps of fwd+autograd-bwd, {ms:.1f} ms/step (oracle/msda_torch_port.py)"}
@@ -355,6 +375,7 @@ def main():
                 "l2_policy": f"rotating {n_sets} distinct input sets ({n_sets * step_bytes / 1e6:.0f} MB nominal, >= 8x the 126 MB L2)",
                 "launch": f"CUDA graph of {chunk} steps x {reps} replays",
                 "sharding": "batch-sharded, no data-path collective",
+                "host": numa_note,
             },
             "roofline": dominant, "roofline_fwd": r_fwd, "roofline_bwd": r_bwd,
             "fwd_only": {"value": w.samples * world / (ms_fwd * 1e-3) / 1e9, "unit": UNIT, "us": ms_fwd * 1e3},
