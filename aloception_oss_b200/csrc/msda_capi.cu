@@ -158,12 +158,16 @@ bool staged_mode_auto(const msda_dims& d) {
   return false;
 }
 
-int sm_count() {
-  static int n = 0;
+int sm_count() {  // of the current device
+  static std::atomic<int> cache[64];
+  int dev = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return 148;
+  std::atomic<int>& slot = cache[dev & 63];
+  int n = slot.load(std::memory_order_relaxed);
   if (n == 0) {
-    int dev = 0, v = 0;
-    if (cudaGetDevice(&dev) == cudaSuccess && cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) n = v;
-    else n = 148;
+    int v = 0;
+    n = (cudaDeviceGetAttribute(&v, cudaDevAttrMultiProcessorCount, dev) == cudaSuccess && v > 0) ? v : 148;
+    slot.store(n, std::memory_order_relaxed);
   }
   return n;
 }
@@ -212,11 +216,15 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
 #define MSDA_FWDS(LPC)                                                                                                 \
   do {                                                                                                                 \
     auto kern = msda::msda_fwd_staged_kernel<T, D, MC, FUSED, 1024, 1, LPC>;                                           \
-    static std::atomic<size_t> smem_set{0}; /* per instantiation: raise the dynamic shared-memory limit when needed */ \
-    if (smem_set.load(std::memory_order_relaxed) < smem) {                                                             \
+    /* per instantiation AND device (function attributes are per context): raise the dynamic shared-memory limit */    \
+    static std::atomic<size_t> smem_set[64];                                                                           \
+    int dev_ = 0;                                                                                                      \
+    cudaGetDevice(&dev_);                                                                                              \
+    std::atomic<size_t>& slot = smem_set[dev_ & 63];                                                                   \
+    if (slot.load(std::memory_order_relaxed) < smem) {                                                                 \
       const cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);       \
       if (ae != cudaSuccess) return fail("msda_forward(staged): cudaFuncSetAttribute(%zu B): %s", smem, cudaGetErrorString(ae)); \
-      smem_set.store(smem, std::memory_order_relaxed);                                                                 \
+      slot.store(smem, std::memory_order_relaxed);                                                                     \
     }                                                                                                                  \
     e = launch_pdl(kern, dim3((unsigned)ctas), dim3((unsigned)threads), smem, st, pdl, (const T*)value, shapes, start,  \
                    (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, d.num_heads, d.num_levels,          \
@@ -319,11 +327,16 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
     if (zc <= 0 || zc > 16) zc = 1;
     long long blocks = ((long long)bytes + chunk - 1) / chunk;
     if (blocks > 148LL * zc) blocks = 148LL * zc;
-    static std::atomic<int> smem_set{0};
-    if (smem_set.load(std::memory_order_relaxed) < chunk) {
-      const cudaError_t ae = cudaFuncSetAttribute(msda::msda_zero_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk);
-      if (ae != cudaSuccess) return fail("zero fill: cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
-      smem_set.store(chunk, std::memory_order_relaxed);
+    if (chunk > 48 * 1024) {  // beyond the default dynamic shared-memory limit: opt in, per device
+      static std::atomic<int> smem_set[64];
+      int dev_ = 0;
+      cudaGetDevice(&dev_);
+      std::atomic<int>& slot = smem_set[dev_ & 63];
+      if (slot.load(std::memory_order_relaxed) < chunk) {
+        const cudaError_t ae = cudaFuncSetAttribute(msda::msda_zero_tma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, chunk);
+        if (ae != cudaSuccess) return fail("zero fill: cudaFuncSetAttribute: %s", cudaGetErrorString(ae));
+        slot.store(chunk, std::memory_order_relaxed);
+      }
     }
     const cudaError_t e = launch_pdl(msda::msda_zero_tma_kernel, dim3((unsigned)blocks), dim3(128), (size_t)chunk, st, false,
                                      (unsigned char*)p, n16, ntail, chunk);

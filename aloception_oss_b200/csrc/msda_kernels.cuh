@@ -61,7 +61,7 @@ template <typename A>
 __device__ __forceinline__ Geo<A> make_geo(A loc_x, A loc_y, int H, int W, bool valid) {
   Geo<A> g;
   // ONE rounding (fused multiply-add): this is what the reference's `loc * size - 0.5` compiles to with nvcc's
-  // default -fmad=true (verified on the B200: tools/debug_gradloc.py), and it is the closest fp32 gets to the
+  // default -fmad=true (verified on the B200: tests/debug_gradloc.py), and it is the closest fp32 gets to the
   // exact coordinate -- floor() decides which pixel pair is interpolated, and grad_loc jumps across that decision.
   const A y = fma(loc_y, (A)H, (A)-0.5);
   const A x = fma(loc_x, (A)W, (A)-0.5);

@@ -4,7 +4,7 @@
 
 The reference ships generic SIMT kernels (alonet/deformable_detr/ops/src/cuda/ms_deform_im2col_cuda.cuh) and no
 Blackwell path; recompiled for sm_100a they are "the reference on the same box" -- the kernels this repository is
-measured against in tools/compare_ref.py.  Nothing of the reference is copied into the repository: the sources
+measured against in tests/compare_ref_cuda.py.  Nothing of the reference is copied into the repository: the sources
 are compiled where they lie, through a scratch copy under /tmp that carries the two edits without which they do
 not build / cannot be loaded next to our operator:
 

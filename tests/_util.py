@@ -85,7 +85,7 @@ def near_floor_discontinuity(loc, shapes, eps=2e-5):
     grad_loc is DISCONTINUOUS there (floor() switches the interpolated pixel pair), so two correct evaluations
     that round ``loc * size - 0.5`` differently (fp32 FMA vs fp32 mul+sub vs fp64) legitimately disagree on
     grad_loc for such a sample -- the reference's own CUDA fp32 kernel and its fp64 evaluation do
-    (tools/debug_gradloc.py).  out, grad_value and grad_attn are continuous and are never masked.
+    (tests/debug_gradloc.py).  out, grad_value and grad_attn are continuous and are never masked.
     """
     loc = np.asarray(loc, dtype=np.float64)
     shapes = np.asarray(shapes, dtype=np.float64)

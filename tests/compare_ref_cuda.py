@@ -1,7 +1,7 @@
 #!/usr/bin/env python3
 """Reference CUDA kernels (rebuilt for sm_100a, oracle/_ref/) vs. this repository's kernels, same inputs, same box.
 
-    python tools/compare_ref.py [--out gpurun_out/compare_ref.jsonl] [--workloads C2,C5DEC,C4DEC,ENC,C5ENC]
+    python tests/compare_ref_cuda.py [--out gpurun_out/compare_ref.jsonl] [--workloads C2,C5DEC,C4DEC,ENC,C5ENC]
 
 For each workload: checks that both implementations agree (fp32), then times forward and backward of each with
 CUDA graphs over rotating input sets.  The reference op is loaded under the torch namespace ``alonet_ref``
