@@ -228,7 +228,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
     }                                                                                                                  \
     e = launch_pdl(kern, dim3((unsigned)ctas), dim3((unsigned)threads), smem, st, pdl, (const T*)value, shapes, start,  \
                    (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, d.num_heads, d.num_levels,          \
-                   d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, (int)tile_rows);             \
+                   d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, (int)tile_rows, spec_on);    \
   } while (0)
     if (d.num_levels * d.num_point == 16 && g_staged_variant.load(std::memory_order_relaxed) != 1) MSDA_FWDS(16); else MSDA_FWDS(0);
 #undef MSDA_FWDS

@@ -921,7 +921,7 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
                        const int32_t* __restrict__ start, const T* __restrict__ loc,
                        const T* __restrict__ attn, T* __restrict__ out,
                        int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
-                       int tile_rows) {
+                       int tile_rows, int spec_on) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
@@ -959,10 +959,13 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
   // ---- per-lane loop invariants: my sample's level ----
   const bool have = lane < LP;
   const LevelMeta lm = load_level_meta(shapes, start, lane, have, inv_p);
-  const bool mine_staged = lane >= s0;
-  const int rowmul = mine_staged ? D : MD;                                // elements per pixel step
-  const int lvl_off = mine_staged ? (lm.st - row0) * D : lm.st * MD;      // element offset of my level's first row
-  const int rs4 = (lm.W * rowmul) << 4;                                   // row stride, pre-shifted for the record
+  const bool mine_staged = have && lane >= s0;  // lanes past L*P publish a zero-weight record on level 0 in GLOBAL memory
+  // speculative regular-window gather (msda_fwd_gather_pass): needs every level at least 2 x 2 pixels
+  const bool spec_ok = spec_on != 0 && __all_sync(0xffffffffu, !have || (lm.H >= 2 && lm.W >= 2));
+  const unsigned xstep = mine_staged ? (unsigned)ROWB : (unsigned)(MD * ES);   // bytes per pixel step in x, of MY sample
+  const unsigned ystep = (unsigned)lm.W * xstep;                               // bytes per row of my level
+  const unsigned lvl_off = (mine_staged ? (unsigned)(lm.st - row0) : (unsigned)lm.st) * xstep;  // my level's first pixel
+  const float fH = (float)lm.H, fW = (float)lm.W;
   const uint32_t tile_s = smem_u32(tile) + (uint32_t)(cl * VEC * ES);
   const int slane = have ? lane : 0;
 
@@ -1027,61 +1030,74 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
       }
     }
     if (q >= Lq) continue;  // warp-uniform
-    const T* __restrict__ vb = value + (long long)(this_bm / M) * S * MD + ((this_bm % M) * D + cl * VEC);
+    const int b = this_bm / M, m = this_bm % M;
+    const char* vbc = reinterpret_cast<const char*>(value + (long long)b * S * MD + (m * D + cl * VEC));
 
-    const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
-    const Geo<float> ge = make_geo<float>(sp.lx, sp.ly, lm.H, lm.W, have);
-    const int off00 = lvl_off + ge.row00 * rowmul;
-    const int rsf = rs4 | (ge.ok11 ? 8 : 0) | (ge.ok10 ? 4 : 0) | (ge.ok01 ? 2 : 0) | (ge.ok00 ? 1 : 0);
-    const float a = sp.a;
-    __syncwarp();
-    rec_a[lane] = make_uint4((unsigned)off00, (unsigned)rsf, __float_as_uint(ge.hy * ge.hx * a), __float_as_uint(ge.hy * ge.lx * a));
-    rec_b[lane] = make_float2(ge.ly * ge.hx * a, ge.ly * ge.lx * a);
-    __syncwarp();
+    bool done = false;
+    if (spec_ok) {
+      const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
+      const float y = fma(sp.ly, fH, -0.5f), x = fma(sp.lx, fW, -0.5f);  // same roundings as make_geo
+      const bool inside = have && y > -1.f && x > -1.f && y < fH && x < fW;
+      const float fy = floorf(y), fx = floorf(x);
+      int y0 = (int)fy, x0 = (int)fx;
+      const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+      float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
+      if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > lm.H - 2) { y0 = lm.H - 2; wy1 = hy; wy0 = 0.f; }
+      if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > lm.W - 2) { x0 = lm.W - 2; wx1 = hx; wx0 = 0.f; }
+      if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; }
+      const float a = sp.a;
+      const unsigned off00 = lvl_off + (unsigned)(y0 * lm.W + x0) * xstep;
+      __syncwarp();
+      rec_a[lane] = make_uint4(off00, ystep, __float_as_uint(wy0 * wx0 * a), __float_as_uint(wy0 * wx1 * a));
+      rec_b[lane] = make_float2(wy1 * wx0 * a, wy1 * wx1 * a);
+      __syncwarp();
 
-    float2 acc[VEC / 2];
+      float2 acc[VEC / 2];
 #pragma unroll
-    for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
-
+      for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+      for (int k0 = 0; k0 < LP; k0 += G) {  // lanes >= LP hold zero-weight records on valid addresses
+        const int src = k0 + g;
+        const uint4 ra = rec_a[src];
+        const float2 rb = rec_b[src];
+        const float wt[4] = {__uint_as_float(ra.z), __uint_as_float(ra.w), rb.x, rb.y};
+        uint4 v[4];
+        if (k0 >= s0 && k0 + G <= LP) {  // whole round in the tile
+          const uint32_t a0 = tile_s + ra.x, a1 = a0 + ra.y;
+          v[0] = lds128_u32(a0); v[1] = lds128_u32(a0 + ROWB); v[2] = lds128_u32(a1); v[3] = lds128_u32(a1 + ROWB);
+        } else if (k0 + G <= s0) {  // whole round in global memory
+          const char* t0 = vbc + ra.x;
+          const char* t1 = t0 + ra.y;
+          const size_t mdb = (size_t)MD * ES;
+          v[0] = ldg128(t0); v[1] = ldg128(t0 + mdb); v[2] = ldg128(t1); v[3] = ldg128(t1 + mdb);
+        } else {  // a round that mixes staged and unstaged levels: generic loads (shared or global window)
+          const bool stg = src >= s0 && src < LP;
+          const char* t0 = (stg ? reinterpret_cast<const char*>(tile + cl * VEC) : vbc) + ra.x;
+          const char* t1 = t0 + ra.y;
+          const size_t xs = stg ? (size_t)ROWB : (size_t)MD * ES;
+          v[0] = *reinterpret_cast<const uint4*>(t0); v[1] = *reinterpret_cast<const uint4*>(t0 + xs);
+          v[2] = *reinterpret_cast<const uint4*>(t1); v[3] = *reinterpret_cast<const uint4*>(t1 + xs);
+        }
 #pragma unroll
-    for (int k0 = 0; k0 < (LPC > 0 ? LPC : 32); k0 += G) {
-      if (LPC == 0 && k0 >= LP) break;
-      const int src = k0 + g;
-      const uint4 ra = rec_a[src];
-      const float2 rb = rec_b[src];
-      const int off = (int)ra.x;
-      int fl = (int)ra.y;
-      if ((LPC == 0 || LPC % G != 0) && src >= LP) fl = 0;
-      const float wt[4] = {__uint_as_float(ra.z), __uint_as_float(ra.w), rb.x, rb.y};
-      const bool all_ok = __all_sync(0xffffffffu, (fl & 15) == 15);
-      uint4 v[4];
-      if (all_ok && k0 >= s0) {  // whole round in the tile
-        const uint32_t a0 = tile_s + (uint32_t)off * ES;
-        const uint32_t a1 = a0 + (uint32_t)(fl >> 4) * ES;
-        v[0] = lds128_u32(a0); v[1] = lds128_u32(a0 + ROWB); v[2] = lds128_u32(a1); v[3] = lds128_u32(a1 + ROWB);
-      } else if (all_ok && k0 + G <= s0) {  // whole round in global memory
-        const T* t0 = vb + off;
-        const T* t1 = vb + (off + (fl >> 4));
-        v[0] = ldg128(t0); v[1] = ldg128(t0 + MD); v[2] = ldg128(t1); v[3] = ldg128(t1 + MD);
-      } else {  // mixed round or some tap invalid: generic loads (shared or global window), zero row for invalid taps
-        const bool stg = src >= s0;
-        const T* t0 = (stg ? tile + cl * VEC : vb) + off;
-        const T* t1 = t0 + (fl >> 4);
-        const int xs = stg ? D : MD;
-        const T* zp = zero_row;
-        const T* tp[4] = {(fl & 1) ? t0 : zp, (fl & 2) ? t0 + xs : zp, (fl & 4) ? t1 : zp, (fl & 8) ? t1 + xs : zp};
+        for (int t = 0; t < 4; ++t) {
+          float f[VEC];
+          Vec16<T>::unpack(v[t], f);
 #pragma unroll
-        for (int t = 0; t < 4; ++t) v[t] = *reinterpret_cast<const uint4*>(tp[t]);
+          for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(wt[t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
+        }
       }
+      constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
+      float o[N_OUT];
+      int first;
+      bool owner;
+      msda_fwd_reduce<T, D>(acc, o, first, owner);
+      bool bad = false;
 #pragma unroll
-      for (int t = 0; t < 4; ++t) {
-        float f[VEC];
-        Vec16<T>::unpack(v[t], f);
-#pragma unroll
-        for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(wt[t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
-      }
+      for (int k = 0; k < N_OUT; ++k) bad = bad || !(fabsf(o[k]) <= 3.402823466e38f);
+      done = !__any_sync(0xffffffffu, bad);
+      if (done && owner) store_vals<T, N_OUT>(o_cur + cl * VEC + first, o);
     }
-    msda_fwd_store<T, D>(o_cur, acc);
+    if (!done)  // a level narrower than 2 pixels, or non-finite sums: the exact zero-line path, out of line
+      msda_fwd_unit_flagged<T, D, MC, FUSED, true>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b, q * M + m, m);
   }
 }
 

@@ -21,7 +21,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--out", default="gpurun_out/staged.jsonl")
     ap.add_argument("--workloads", default="ENC,C5ENC")
-    ap.add_argument("--warps", default="0")
+    ap.add_argument("--warps", default="0,24")
     ap.add_argument("--kb", default="0")
     ap.add_argument("--variants", default="0,1")
     ap.add_argument("--dtype", default="f32")
