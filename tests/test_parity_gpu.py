@@ -241,6 +241,22 @@ def test_tma_staged_forward_full_size_encoder_call(cuda_device):
     assert torch.equal(got, base)
 
 
+@pytest.mark.parametrize("channels", [30, 32, 64, 71])
+def test_gradient_numerical_like_the_reference_op_test(channels, cuda_device):
+    """The reference's own gradient test (alonet/deformable_detr/ops/test.py:88-131): torch.autograd.gradcheck through
+    MSDeformAttnFunction in float64 at N, M = 1, 2; Lq, L, P = 2, 2, 2; levels (6,4), (3,2); D in {30, 32, 64, 71}."""
+    N, M, Lq, L, P = 1, 2, 2, 2, 2
+    shapes = torch.as_tensor([(6, 4), (3, 2)], dtype=torch.int32, device=cuda_device)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1].to(torch.int32)))
+    S = int((shapes[:, 0] * shapes[:, 1]).sum())
+    torch.manual_seed(3)
+    value = (torch.rand(N, S, M, channels, device=cuda_device) * 0.01).double().requires_grad_(True)
+    loc = torch.rand(N, Lq, M, L, P, 2, device=cuda_device).double().requires_grad_(True)
+    attn = torch.rand(N, Lq, M, L, P, device=cuda_device) + 1e-5
+    attn = (attn / attn.sum(-1, keepdim=True).sum(-2, keepdim=True)).double().requires_grad_(True)
+    assert torch.autograd.gradcheck(msda.MSDeformAttnFunction.apply, (value, shapes, start, loc, attn, 2))
+
+
 # ---------------------------------------------------------------------------------------------------------
 # edge cases
 # ---------------------------------------------------------------------------------------------------------
