@@ -54,6 +54,7 @@ struct Geo {
   int row00;         // y0 * W + x0 (may be "negative-ish"; only used for valid taps)
   int W;
   bool ok00, ok01, ok10, ok11;  // tap inside the level AND sample inside the window
+  bool inside;                  // sample inside the (-1, size) window; false also for NaN / Inf coordinates
 };
 
 // `valid` = this lane group really has a sample (tail predicate).
@@ -79,6 +80,11 @@ __device__ __forceinline__ Geo<A> make_geo(A loc_x, A loc_y, int H, int W, bool 
   g.ok01 = inside && y0ok && x1ok;
   g.ok10 = inside && y1ok && x0ok;
   g.ok11 = inside && y1ok && x1ok;
+  g.inside = inside;
+  if (!inside) {  // the reference skips such a sample altogether: no NaN / Inf coordinate may leak into a 0 * x product
+    g.ly = g.lx = g.hy = g.hx = (A)0;
+    g.row00 = 0;
+  }
   return g;
 }
 
@@ -519,8 +525,8 @@ msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have
     float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
     if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > sp.H - 2) { y0 = sp.H - 2; wy1 = hy; wy0 = 0.f; }
     if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > sp.W - 2) { x0 = sp.W - 2; wx1 = hx; wx0 = 0.f; }
-    if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; }
-    const float a = sp.a;
+    if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; wx0 = 0.f; wx1 = 0.f; }  // (NaN / Inf coordinates land here too)
+    const float a = inside ? sp.a : 0.f;
     const float w00 = wy0 * wx0 * a, w01 = wy0 * wx1 * a, w10 = wy1 * wx0 * a, w11 = wy1 * wx1 * a;
     // BYTE offsets from the unit's base pointer (32-bit: the host checks S*M*D*sizeof(T) <= 2^29): a tap pointer is then
     // one 64-bit add instead of an index add + scale + carry chain
@@ -580,7 +586,7 @@ msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have
   SampleGeo sg;
   Geo<float> ge;
   finish_geometry(sp, have, MD, sg, ge);
-  const float a = sp.a;
+  const float a = ge.inside ? sp.a : 0.f;  // an outside sample contributes exactly nothing, whatever its weight is
   const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
   if constexpr (SR) {
     __syncwarp();  // the previous pass / the previous unit of this warp has finished reading the records
@@ -1044,8 +1050,8 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
       float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
       if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > lm.H - 2) { y0 = lm.H - 2; wy1 = hy; wy0 = 0.f; }
       if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > lm.W - 2) { x0 = lm.W - 2; wx1 = hx; wx0 = 0.f; }
-      if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; }
-      const float a = sp.a;
+      if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; wx0 = 0.f; wx1 = 0.f; }
+      const float a = inside ? sp.a : 0.f;
       const unsigned off00 = lvl_off + (unsigned)(y0 * lm.W + x0) * xstep;
       __syncwarp();
       rec_a[lane] = make_uint4(off00, ystep, __float_as_uint(wy0 * wx0 * a), __float_as_uint(wy0 * wx1 * a));
@@ -1164,7 +1170,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
       sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
     }
     finish_geometry(sp, have, MD, sg, ge);
-    const float a = sp.a;
+    const float a = (FUSED || ge.inside) ? sp.a : 0.f;  // outside sample: every gradient is exactly zero (FUSED keeps the softmax weight)
     const int H = sp.H, W = sp.W;
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
@@ -1320,7 +1326,7 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__
       for (int p = 0; p < P; ++p) {
         const int s = l * P + p;
         const Geo<A> ge = make_geo<A>(to_acc(u_loc[2 * s]), to_acc(u_loc[2 * s + 1]), H, W, true);
-        const A a = to_acc(u_att[s]);
+        const A a = ge.inside ? to_acc(u_att[s]) : (A)0;
         const T* t0 = lv + (long long)ge.row00 * MD;
         const long long rs = (long long)W * MD;
         const A v00 = (cok && ge.ok00) ? to_acc(t0[0]) : (A)0;
@@ -1360,7 +1366,7 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
     for (int p = 0; p < P; ++p) {
       const int s = l * P + p;
       const Geo<A> ge = make_geo<A>(to_acc(u_loc[2 * s]), to_acc(u_loc[2 * s + 1]), H, W, true);
-      const A a = to_acc(u_att[s]);
+      const A a = ge.inside ? to_acc(u_att[s]) : (A)0;
       const long long o00 = loff + (long long)ge.row00 * MD;
       const long long rs = (long long)W * MD;
       const A w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;

@@ -70,3 +70,27 @@ def test_c_oracle_f64_of_f32_inputs_is_the_headroom_reference():
     out = msda_oracle.forward(x["value"].astype(np.float64), x["shapes"], x["loc"].astype(np.float64),
                               x["attn"].astype(np.float64), x["start"])
     assert_close(out, ref["out64"], 2e-7, 1e-10)
+
+
+def test_oracle_drops_samples_with_wild_locations():
+    """NaN / Inf / huge sampling locations fail the reference's window test (ms_deform_im2col_cuda.cuh:285-291) and are
+    skipped: same result as the same call with those samples given zero weight on a harmless location."""
+    import torch
+
+    from aloception_oss_b200.synthetic import Workload, torch_inputs
+
+    w = Workload("wild", 1, ((5, 6), (3, 3)), 7, M=2, P=3, D=4)
+    x = {k: (v.double().numpy() if v.is_floating_point() else v.numpy()) for k, v in torch_inputs(w, seed=5, loc_mode="wide").items()}
+    mask = np.zeros(x["loc"].shape[:-1], dtype=bool)
+    mask.reshape(-1)[::3] = True
+    wild = np.array([np.nan, np.inf, -np.inf, 1e30, -1e30, 3e9, -7.5])
+    x["loc"][mask] = wild[np.arange(mask.sum()) % wild.size][:, None]
+    y = {k: v.copy() for k, v in x.items()}
+    y["attn"][mask] = 0.0
+    y["loc"][mask] = 0.5
+    got = msda_oracle.forward(x["value"], x["shapes"], x["loc"], x["attn"], x["start"])
+    want = msda_oracle.forward(y["value"], y["shapes"], y["loc"], y["attn"], y["start"])
+    assert np.isfinite(got).all() and np.array_equal(got, want)
+    g = msda_oracle.backward(x["grad_out"], x["value"], x["shapes"], x["loc"], x["attn"], x["start"])
+    gw = msda_oracle.backward(y["grad_out"], y["value"], y["shapes"], y["loc"], y["attn"], y["start"])
+    assert np.array_equal(g[0], gw[0]) and not g[2][mask].any() and not g[1][mask].any()

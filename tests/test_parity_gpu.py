@@ -280,6 +280,31 @@ def test_all_samples_outside_gives_zero(cuda_device):
     assert not out.any() and not gv.any() and not gl.any() and not ga.any()
 
 
+@pytest.mark.parametrize("spec", [1, 2], ids=["flagged", "speculative"])
+def test_wild_locations_contribute_nothing(spec, cuda_device):
+    """NaN, +-Inf and astronomically large sampling locations fall outside every level: such samples contribute exactly
+    zero to out / grad_value / grad_attn (the reference's window test is false for them), on both forward gather paths."""
+    w = Workload("wild", 2, ((9, 11), (5, 6), (3, 3)), 40, M=8, P=4, D=32)
+    x = torch_inputs(w, seed=5, loc_mode="wide")
+    wild = torch.tensor([float("nan"), float("inf"), float("-inf"), 1e30, -1e30, 3e9, -7.5])
+    loc = x["loc"]
+    mask = torch.zeros(loc.shape[:-1], dtype=torch.bool)
+    mask.view(-1)[::3] = True  # every third sample is wild
+    loc[mask] = wild[torch.arange(int(mask.sum())) % wild.numel()].unsqueeze(-1).expand(-1, 2)
+    x["loc"] = loc.contiguous()
+    _capi.set_tuning("spec_mode", spec)
+    out, gv, gl, ga = run_op(x, cuda_device)
+    # reference semantics: drop the wild samples (zero attention weight on a harmless location)
+    y = {k: v.clone() for k, v in x.items()}
+    y["attn"][mask] = 0.0
+    y["loc"][mask] = 0.5
+    want = oracle64(y)
+    assert np.isfinite(out).all() and np.isfinite(gv).all()
+    assert_close(out, want[0], 1e-4, 1e-7 * rms(want[0]), "out")
+    check_grad_value(gv, {"grad_value": want[1]}, 1e-4)
+    assert not ga[mask.numpy()].any()
+
+
 @pytest.mark.parametrize("field,val", [("N", 0), ("Lq", 0)])
 def test_empty_inputs(field, val, cuda_device):
     base = dict(N=2, Lq=5)
