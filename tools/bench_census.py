@@ -7,6 +7,10 @@ is split over the ranks (N = 32 / world per GPU), no collective on the data path
     python tools/bench_census.py                      # 1 GPU
     python -m torch.distributed.run --nnodes=1 --nproc-per-node 8 --master-addr 127.0.0.1 --master-port 29530 tools/bench_census.py
 
+``--train``: BASELINE.json configs[4] instead -- the 6 + 6 forward AND backward calls of one training step at the reference's
+per-GPU batch of 2 (B = 16 on 8 GPUs, WEAK scaling: every rank has its own 2 images; the DDP gradient all-reduce of the model is
+outside the operator).
+
 Prints one JSON line on rank 0 (device time, max over ranks)."""
 import json
 import os
@@ -29,7 +33,8 @@ def main():
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
     msda.load_ops()
-    n_local = GLOBAL_BATCH // world
+    train = "--train" in sys.argv
+    n_local = 2 if train else GLOBAL_BATCH // world
     enc = WORKLOADS["C4ENC"].with_batch(n_local)
     dec = WORKLOADS["C4DEC"].with_batch(n_local)
     # two input sets per shape: 6 layers alternate between them (each layer of the real model has its own activations)
@@ -37,11 +42,18 @@ def main():
     dec_sets = [device_inputs(dec, seed=100 * rank + 10 + i, device=dev, loc_mode="unit") for i in range(2)]
     fwd = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
 
+    bwd = lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
+
     def forward_pass():
         for i in range(6):
             fwd(enc_sets[i % 2])
         for i in range(6):
             fwd(dec_sets[i % 2])
+        if train:
+            for i in range(6):
+                bwd(dec_sets[i % 2])
+            for i in range(6):
+                bwd(enc_sets[i % 2])
 
     for _ in range(3):
         forward_pass()
@@ -66,12 +78,15 @@ def main():
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
-    samples = GLOBAL_BATCH * 6 * (enc.Lq + dec.Lq) * enc.M * enc.L * enc.P
+    samples = (n_local * world) * 6 * (enc.Lq + dec.Lq) * enc.M * enc.L * enc.P
     if rank == 0:
+        what = "fwd+bwd" if train else "forward"
         print(json.dumps({
-            "metric": "MSDeformAttn forward Gsamples/s, DeformableDETR-R50 operator census (6 encoder + 6 decoder calls), B=32 800x1333",
-            "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "n_gpus": world, "ms_per_forward": ms, "scaling": "strong",
-            "per_gpu_batch": n_local, "dtype": "f32", "data": "synthetic", "launch": f"CUDA graph of {reps} forwards (12 launches each)",
+            "metric": f"MSDeformAttn {what} Gsamples/s, DeformableDETR-R50 operator census (6 encoder + 6 decoder calls), "
+                      f"B={n_local * world} 800x1333",
+            "value": samples / (ms * 1e-3) / 1e9, "unit": "Gsamples/s", "n_gpus": world, "ms_per_step" if train else "ms_per_forward": ms,
+            "scaling": "weak" if train else "strong", "per_gpu_batch": n_local, "dtype": "f32", "data": "synthetic",
+            "launch": f"CUDA graph of {reps} passes ({36 if train else 12} launches each)",
         }), flush=True)
     if world > 1:
         dist.destroy_process_group()
