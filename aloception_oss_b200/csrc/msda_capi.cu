@@ -131,6 +131,7 @@ bool vec_shape_ok(const msda_dims& d) {
 }
 
 int head_major_for(const msda_dims& d) {
+  (void)d;  // no shape-dependent rule: head-major ordering measured +-1 % (profiles/r1_sweep_head_major.jsonl)
   const int k = g_head_major.load(std::memory_order_relaxed);
   if (k == 1) return 0;
   if (k == 2) return 1;
