@@ -19,7 +19,7 @@ namespace {
 
 thread_local char g_err[256] = "";
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_variant{0};  // 0 = default (tile kernel for m = 24), 1 = register kernels only, 2 = generic kernel only
+std::atomic<int> g_variant{0};  // 0 = default (balanced tile kernel for m = 24), 1 = register kernels, 2 = generic kernel, 3 = unbalanced tile kernel
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -186,19 +186,34 @@ __device__ __forceinline__ bool before_q(float x1, float y1, float q1, float x2,
 
 __device__ __forceinline__ uint32_t sv_smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
+// BAL: in-CTA load balancing.  The selection costs c * num_valid comparator pairs and c varies from polygon to polygon (0 for
+// disjoint boxes ... 8), so a warp whose lanes own consecutive polygons idles most lanes while the largest polygon finishes
+// (measured: 9.7 of 32 lanes active).  With BAL the CTA counting-sorts its 128 polygons by c (shared-memory atomics, 9
+// buckets; c is known from the mask before anything is compacted), every owner writes its compacted candidates into the
+// column of its SORTED position, thread t runs the selection of column t (conflict-free 128-bit reads, near-uniform trip
+// counts inside a warp) and hands the packed order word back to the owner through shared memory.
+// Shared memory: the compacted columns take the place of the staged vertices (the owner carries its <= 8 candidates in
+// registers across the barrier that retires the tile), so a CTA needs 29.7 KB and 7 CTAs = 28 warps fit an SM.
+template <bool BAL>
 __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restrict__ vertices, const uint8_t* __restrict__ mask,
                                                            const int32_t* __restrict__ num_valid, int32_t* __restrict__ idx,
                                                            long long total) {
   constexpr int M = 24;
-  __shared__ __align__(128) float2 s_v[kTile * M];        // 24 576 B; reused for the indices at the end
-  __shared__ __align__(16) uint8_t s_m[kTile * M];        //  3 072 B
-  __shared__ __align__(16) int32_t s_nv[kTile];           //    512 B
-  __shared__ __align__(16) float4 s_slot[kSlots][kTile];  // 16 384 B: column t = thread t's compacted candidates
+  // 24 576 B: staged vertices; then the columns s_slot[kSlots + 1][kTile] (18 432 B; column p = candidates (x, y, q, index)
+  // of the polygon at sorted position p, row kSlots = (vertex 0, its q, c | rounds << 8)); then the indices (4 608 B)
+  __shared__ __align__(128) float2 s_v[kTile * M];
+  __shared__ __align__(16) uint8_t s_m[kTile * M];  //  3 072 B
+  __shared__ __align__(16) int32_t s_nv[kTile];     //    512 B
+  __shared__ unsigned long long s_order[kTile];     //  1 024 B: packed result, indexed by owner
+  __shared__ int s_owner[kTile];                    //    512 B: owner thread of the polygon at sorted position p (-1: none)
+  __shared__ int s_cnt[kSlots + 1];
   __shared__ __align__(8) unsigned long long s_bar;
+  float4(*s_slot)[kTile] = reinterpret_cast<float4(*)[kTile]>(s_v);
   const int t = threadIdx.x;
   const long long p0 = (long long)blockIdx.x * kTile;
   const int rows = total - p0 < (long long)kTile ? (int)(total - p0) : kTile;
 
+  if (BAL && t <= kSlots) s_cnt[t] = 0;
   if (rows == kTile) {
     if (t == 0) {
       asm volatile("mbarrier.init.shared::cta.b64 [%0], 1;" ::"r"(sv_smem_u32(&s_bar)) : "memory");
@@ -228,7 +243,14 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
     __syncthreads();
   }
 
-  int o[kIdx];
+  // ---- phase A (owner thread): mask bits, pad index, candidates into registers; polygons the fast path cannot take are finished
+  int pad = 0, nv_in = 0, nv = 0, c = 0;
+  unsigned long long order = 0;  // idx[j] in bits [5j, 5j + 5)
+  bool fast = false;             // selection still to be run over the compacted column
+  const float y0 = -kF;          // (float)(-EPSILON), sort_vert_kernel.cu:78-79
+  const float q0 = q_of(1.f, y0);
+  float4 cand[kSlots];
+  float4 head = make_float4(0.f, 0.f, 0.f, 0.f);
   if (t < rows) {
     unsigned valid = 0;
     {
@@ -236,7 +258,7 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
 #pragma unroll
       for (int k = 0; k < M / 8; ++k) {
         const uint2 w = mw[k];
-        // byte != 0 -> bit: OR the byte's bits down to bit 0, then gather the four bit-0s
+        // byte != 0 -> bit: OR the byte's bits down to its bit 0, then gather the four bit-0s with one multiply
         unsigned lo = w.x | (w.x >> 4); lo |= lo >> 2; lo |= lo >> 1; lo &= 0x01010101u;
         unsigned hi = w.y | (w.y >> 4); hi |= hi >> 2; hi |= hi >> 1; hi &= 0x01010101u;
         const unsigned b4lo = (lo * 0x01020408u) >> 24 & 0xfu;  // bytes 0..3 -> bits 0..3
@@ -245,71 +267,110 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
       }
     }
     const unsigned inv = ~valid & 0x00ffffffu & ~((1u << kOff) - 1u);
-    const int pad = inv ? (__ffs(inv) - 1) : M - 1;  // sort_vert_kernel.cu:56-62
-    const int nv_in = s_nv[t];
+    pad = inv ? (__ffs(inv) - 1) : M - 1;  // sort_vert_kernel.cu:56-62
+    nv_in = s_nv[t];
+    nv = nv_in > kIdx - 1 ? kIdx - 1 : nv_in;
+    c = __popc(valid);
+    const float2* v = s_v + t * M;
+    if (nv_in >= 3 && c <= kSlots) {
+      fast = true;
+      unsigned bits = valid;
+#pragma unroll
+      for (int i = 0; i < kSlots; ++i) {
+        if (i < c) {
+          const int k = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float2 xy = v[k];
+          cand[i] = make_float4(xy.x, xy.y, q_of(xy.x, xy.y), __int_as_float(k));
+        }
+      }
+      const float2 v0 = v[0];
+      head = make_float4(v0.x, v0.y, q_of(v0.x, v0.y), __int_as_float(c | (nv << 8)));
+    } else if (nv_in >= 3) {  // more than 8 valid candidates: same scan over the staged tile
+      float px = 0.f, py = 0.f, pq = 0.f;
+      for (int j = 0; j < nv; ++j) {
+        float x_min = 1.f, y_min = y0, q_min = q0;
+        int take = -1;
+        unsigned bits = valid;
+        while (bits) {
+          const int k = __ffs(bits) - 1;
+          bits &= bits - 1;
+          const float2 xy = v[k];
+          const float q = q_of(xy.x, xy.y);
+          if (before_q(xy.x, xy.y, q, x_min, y_min, q_min) && (j == 0 || before_q(px, py, pq, xy.x, xy.y, q))) {
+            x_min = xy.x; y_min = xy.y; q_min = q; take = k;
+          }
+        }
+        if (take < 0) {  // nothing selected: idx[j] = 0 and the next round compares against vertex 0
+          take = 0;
+          const float2 xy = v[0];
+          px = xy.x; py = xy.y; pq = q_of(px, py);
+        } else {
+          px = x_min; py = y_min; pq = q_min;
+        }
+        order |= (unsigned long long)take << (5 * j);
+      }
+    }
+  }
+
+  // ---- sorted position of this thread's polygon; the staged tile retires, the columns take its place
+  int position = t;
+  if constexpr (BAL) {
+    const int key = fast ? c : 0;  // bucket 0 also holds the polygons with nothing left to do
+    const int pos = atomicAdd(&s_cnt[key], 1);
+    __syncthreads();
+    int base = 0;
+#pragma unroll
+    for (int k = 0; k < kSlots; ++k) base += k < key ? s_cnt[k] : 0;
+    position = base + pos;
+  } else {
+    __syncthreads();
+  }
+  if (fast) {
+#pragma unroll
+    for (int i = 0; i < kSlots; ++i)
+      if (i < c) s_slot[i][position] = cand[i];
+    s_slot[kSlots][position] = head;
+  }
+  s_owner[position] = fast ? t : -1;
+  __syncthreads();
+
+  // ---- phase B: the selection rounds over column t
+  {
+    const int owner = s_owner[t];
+    if (owner >= 0) {
+      const float4 h = s_slot[kSlots][t];
+      const int cc = __float_as_int(h.w) & 0xff, rounds = __float_as_int(h.w) >> 8;
+      unsigned long long ord = 0;
+      float px = 0.f, py = 0.f, pq = 0.f;
+      for (int j = 0; j < rounds; ++j) {
+        float x_min = 1.f, y_min = y0, q_min = q0;
+        int take = -1;
+        for (int i = 0; i < cc; ++i) {
+          const float4 s = s_slot[i][t];
+          const bool sel = before_q(s.x, s.y, s.z, x_min, y_min, q_min) & ((j == 0) | before_q(px, py, pq, s.x, s.y, s.z));
+          x_min = sel ? s.x : x_min; y_min = sel ? s.y : y_min; q_min = sel ? s.z : q_min;
+          take = sel ? __float_as_int(s.w) : take;
+        }
+        // nothing selected: idx[j] = 0 and the next round compares against vertex 0
+        const bool none = take < 0;
+        px = none ? h.x : x_min; py = none ? h.y : y_min; pq = none ? h.z : q_min;
+        ord |= (unsigned long long)(none ? 0 : take) << (5 * j);
+      }
+      s_order[owner] = ord;
+    }
+  }
+  __syncthreads();  // results published; the columns retire, the indices take their place
+  if (fast) order = s_order[t];
+
+  // ---- phase C (owner thread): close the polygon, pad, identical-boxes corner case; coalesced store
+  int32_t* s_idx = reinterpret_cast<int32_t*>(s_v);
+  if (t < rows) {
+    int o[kIdx];
     if (nv_in < 3) {
 #pragma unroll
       for (int j = 0; j < kIdx; ++j) o[j] = pad;
     } else {
-      const int nv = nv_in > kIdx - 1 ? kIdx - 1 : nv_in;
-      const float2* v = s_v + t * M;
-      const int c = __popc(valid);
-      const float y0 = -kF;  // (float)(-EPSILON), sort_vert_kernel.cu:78-79
-      const float q0 = q_of(1.f, y0);
-      float px = 0.f, py = 0.f, pq = 0.f;
-      unsigned long long order = 0;  // idx[j] in bits [5j, 5j + 5)
-      if (c <= kSlots) {
-        {
-          unsigned bits = valid;
-          int cnt = 0;
-          while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const float2 xy = v[k];
-            s_slot[cnt][t] = make_float4(xy.x, xy.y, q_of(xy.x, xy.y), __int_as_float(k));
-            ++cnt;
-          }
-        }
-        const float2 v0 = v[0];
-        const float qv0 = q_of(v0.x, v0.y);
-        for (int j = 0; j < nv; ++j) {
-          float x_min = 1.f, y_min = y0, q_min = q0;
-          int take = -1;
-          for (int i = 0; i < c; ++i) {
-            const float4 s = s_slot[i][t];
-            const bool sel = before_q(s.x, s.y, s.z, x_min, y_min, q_min) & ((j == 0) | before_q(px, py, pq, s.x, s.y, s.z));
-            x_min = sel ? s.x : x_min; y_min = sel ? s.y : y_min; q_min = sel ? s.z : q_min;
-            take = sel ? __float_as_int(s.w) : take;
-          }
-          // nothing selected: idx[j] = 0 and the next round compares against vertex 0
-          const bool none = take < 0;
-          px = none ? v0.x : x_min; py = none ? v0.y : y_min; pq = none ? qv0 : q_min;
-          order |= (unsigned long long)(none ? 0 : take) << (5 * j);
-        }
-      } else {  // more than 8 valid candidates: same scan over the staged tile
-        for (int j = 0; j < nv; ++j) {
-          float x_min = 1.f, y_min = y0, q_min = q0;
-          int take = -1;
-          unsigned bits = valid;
-          while (bits) {
-            const int k = __ffs(bits) - 1;
-            bits &= bits - 1;
-            const float2 xy = v[k];
-            const float q = q_of(xy.x, xy.y);
-            if (before_q(xy.x, xy.y, q, x_min, y_min, q_min) && (j == 0 || before_q(px, py, pq, xy.x, xy.y, q))) {
-              x_min = xy.x; y_min = xy.y; q_min = q; take = k;
-            }
-          }
-          if (take < 0) {
-            take = 0;
-            const float2 xy = v[0];
-            px = xy.x; py = xy.y; pq = q_of(px, py);
-          } else {
-            px = x_min; py = y_min; pq = q_min;
-          }
-          order |= (unsigned long long)take << (5 * j);
-        }
-      }
 #pragma unroll
       for (int jj = 0; jj < kIdx - 1; ++jj) o[jj] = (int)((order >> (5 * jj)) & 31ull);
       // close the polygon (sort_vert_kernel.cu:104), pad (:107-109)
@@ -329,10 +390,6 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
         }
       }
     }
-  }
-  __syncthreads();  // every thread is done with its rows of s_v: the indices take their place
-  int32_t* s_idx = reinterpret_cast<int32_t*>(s_v);
-  if (t < rows) {
 #pragma unroll
     for (int j = 0; j < kIdx; ++j) s_idx[t * kIdx + j] = o[j];
   }
@@ -402,7 +459,7 @@ const char* sortv_last_error_string(void) { return g_err; }
 uint64_t sortv_kernel_launch_count(void) { return g_launches.load(); }
 
 int sortv_set_variant(int variant) {
-  if (variant < 0 || variant > 2) return fail("sortv_set_variant: unknown variant %d", variant);
+  if (variant < 0 || variant > 3) return fail("sortv_set_variant: unknown variant %d", variant);
   g_variant.store(variant);
   return 0;
 }
@@ -421,10 +478,11 @@ int sortv_sort_vertices(const float* vertices, const uint8_t* mask, const int32_
   const bool a16 = (reinterpret_cast<uintptr_t>(vertices) % 16) == 0 && (reinterpret_cast<uintptr_t>(mask) % 8) == 0;
   const bool tma_ok = a16 && (reinterpret_cast<uintptr_t>(mask) % 16) == 0 && (reinterpret_cast<uintptr_t>(num_valid) % 16) == 0 &&
                       (reinterpret_cast<uintptr_t>(idx) % 16) == 0;
-  if (m == 24 && tma_ok && g_variant == 0) sortv_tile_kernel<<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total);
-  else if (m == 24 && a16 && g_variant <= 1) sortv_kernel<24><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
-  else if (m == 16 && a16 && g_variant <= 1) sortv_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
-  else if (m == 32 && a16 && g_variant <= 1) sortv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
+  if (m == 24 && tma_ok && g_variant == 0) sortv_tile_kernel<true><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total);
+  else if (m == 24 && tma_ok && g_variant == 3) sortv_tile_kernel<false><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total);
+  else if (m == 24 && a16 && g_variant != 2) sortv_kernel<24><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
+  else if (m == 16 && a16 && g_variant != 2) sortv_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
+  else if (m == 32 && a16 && g_variant != 2) sortv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
   else sortv_kernel_generic<<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total, m);
   const cudaError_t e = cudaPeekAtLastError();
   if (e != cudaSuccess) {

@@ -66,7 +66,7 @@ def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--ref", action="store_true")
     ap.add_argument("--cpu", action="store_true")
-    ap.add_argument("--variant", type=int, default=0, help="sortv_set_variant: 0 tile kernel, 1 register kernel, 2 generic")
+    ap.add_argument("--variant", type=int, default=0, help="sortv_set_variant: 0 balanced tile kernel, 1 register kernel, 2 generic, 3 unbalanced tile kernel")
     args = ap.parse_args()
     assert torch.cuda.is_available(), "needs a CUDA device (no CPU fallback)"
     dev = torch.device("cuda:0")
