@@ -45,3 +45,40 @@ def test_plain_c_program_matches_the_oracle(tmp_path, cuda_device):
     assert "C ABI smoke: OK" in res.stdout
     for name in ("forward", "grad_value", "grad_attn", "grad_loc", "forward_host", "plugin_twin"):
         assert f"{name:<12s} ok" in res.stdout, res.stdout
+
+
+# ------------------------------------------------------------------ include/sortv_b200.h
+
+SORTV_SRC = os.path.join(ROOT, "tests", "c_abi", "sortv_smoke.c")
+
+
+def build_sortv(tmp_path):
+    from aloception_oss_b200 import rotated_iou
+    from oracle import sortv_oracle
+
+    rotated_iou.build_library()
+    sortv_oracle.build()
+    exe = str(tmp_path / "sortv_smoke")
+    pkg, ora = os.path.join(ROOT, "aloception_oss_b200"), os.path.join(ROOT, "oracle")
+    cmd = ["gcc", "-std=c11", "-O1", "-Wall", "-Werror", "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CUDA, "include"),
+           SORTV_SRC, "-o", exe, "-L" + pkg, "-lsortv_b200", "-L" + ora, "-lsortv_oracle", "-L" + os.path.join(CUDA, "lib64"),
+           "-lcudart", "-lm", "-Wl,-rpath," + pkg, "-Wl,-rpath," + ora, "-Wl,-rpath," + os.path.join(CUDA, "lib64")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="needs gcc")
+def test_sortv_plain_c_program_compiles_and_links(tmp_path):
+    assert os.path.exists(build_sortv(tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(shutil.which("gcc") is None, reason="needs gcc")
+def test_sortv_plain_c_program_matches_the_oracle(tmp_path, cuda_device):
+    exe = build_sortv(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "sortv C ABI smoke: OK" in res.stdout
+    for v in range(4):
+        assert f"variant {v}     ok" in res.stdout, res.stdout
