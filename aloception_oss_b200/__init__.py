@@ -8,6 +8,7 @@ ops/modules/__init__.py:9):
 from .functions import (  # noqa: F401
     MSDeformAttnFunction,
     MSDeformAttnFusedFunction,
+    begin_backward_zero_fill,
     fused_supported,
     ms_deform_attn_fused_backward,
     ms_deform_attn_fused_forward,
@@ -23,6 +24,6 @@ from . import transformer  # noqa: F401  (encoder / decoder layer loop around th
 __all__ = [
     "MSDeformAttnFunction", "ms_deform_attn_core_pytorch", "load_MultiScaleDeformableAttention", "load_ops",
     "MSDeformAttn", "ms_deform_attn_forward", "ms_deform_attn_backward", "MSDeformAttnFusedFunction",
-    "ms_deform_attn_fused_forward", "ms_deform_attn_fused_backward", "fused_supported",
+    "ms_deform_attn_fused_forward", "ms_deform_attn_fused_backward", "fused_supported", "begin_backward_zero_fill",
 ]
 __version__ = "0.1.0"

@@ -19,6 +19,7 @@ HEADER = os.path.join(ROOT, "include", "msda_b200.h")
 
 ABI_VERSION = 1
 F32, BF16, F16, F64 = 0, 1, 2, 3
+BWD_PREZEROED = 1  # MSDA_BWD_PREZEROED
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -88,6 +89,8 @@ def lib() -> ctypes.CDLL:
     L.msda_backward_workspace_bytes.argtypes = [dp, i]
     L.msda_backward.restype = i
     L.msda_backward.argtypes = [vp] * 10 + [sz, dp, i, i, vp]
+    L.msda_zero_fill.restype = i
+    L.msda_zero_fill.argtypes = [vp, sz, vp]
     L.msda_im2col_inference.restype = i
     L.msda_im2col_inference.argtypes = [vp] * 6 + [i] * 7 + [vp, i]
     L.msda_fused_supported.restype = i

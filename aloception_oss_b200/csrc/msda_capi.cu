@@ -307,6 +307,10 @@ int forward_typed(const void* value, const int32_t* shapes, const int32_t* start
 // ---------------------------------------------------------------------------------------------
 // backward dispatch
 // ---------------------------------------------------------------------------------------------
+// set for the duration of one msda_backward call: the caller zeroed the accumulation buffer itself
+// (MSDA_BWD_PREZEROED), so the fill is skipped and the scatter kernel is launched without the programmatic dependency
+thread_local bool t_prezeroed = false;
+
 int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   if (bytes == 0) return 0;
   if (!aligned(p, 16)) {  // odd views: let the driver do it
@@ -372,7 +376,7 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   // Only when the fill is short (grad_value fits in L2): behind a long fill the early-launched CTAs would just sit on
   // the SMs the fill needs (C4DEC, 728 MB: 298 us with PDL vs 290 us without).
   const size_t fill_bytes = sizeof(float) * (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
-  const bool pdl = !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20);
+  const bool pdl = !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20) && !t_prezeroed;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
@@ -402,7 +406,8 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
   const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
   constexpr bool needs_ws = sizeof(T) != sizeof(A);
   A* acc = needs_ws ? (A*)workspace : (A*)grad_value;
-  if (int rc = zero_fill(acc, n_value * sizeof(A), st)) return rc;
+  if (!t_prezeroed)
+    if (int rc = zero_fill(acc, n_value * sizeof(A), st)) return rc;
   if (units > 0 && d.channels > 0 && d.num_levels * d.num_point > 0) {
     bool done = false;
     if constexpr (!std::is_same<T, double>::value) {
@@ -612,7 +617,11 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
                   size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream) {
   g_err[0] = 0;
   if (int rc = validate_dims(dims, dtype)) return rc;
-  if (flags != 0) return fail("flags must be 0");
+  if (flags & ~MSDA_BWD_PREZEROED) return fail("unknown flags 0x%x", flags);
+  struct Prezeroed {  // scoped: every return path clears it
+    explicit Prezeroed(bool v) { t_prezeroed = v; }
+    ~Prezeroed() { t_prezeroed = false; }
+  } prezeroed_scope((flags & MSDA_BWD_PREZEROED) != 0);
   const msda_dims& d = *dims;
   const long long units = (long long)d.batch * d.num_query * d.num_heads;
   const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
@@ -635,6 +644,16 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
     case MSDA_F64: return backward_typed<double>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
   }
   return fail("unreachable");
+}
+
+int msda_zero_fill(void* ptr, size_t bytes, void* stream) {
+  g_err[0] = 0;
+  if (bytes > 0 && !ptr) return fail("NULL pointer passed to msda_zero_fill");
+  const bool keep = t_prezeroed;
+  t_prezeroed = false;
+  const int rc = zero_fill(ptr, bytes, (cudaStream_t)stream);
+  t_prezeroed = keep;
+  return rc;
 }
 
 int msda_forward_host(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,

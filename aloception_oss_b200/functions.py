@@ -25,6 +25,12 @@ from torch.autograd.function import once_differentiable
 
 from . import _capi
 
+# MSDA_EARLY_ZERO_FILL=1: MSDeformAttnFunction starts the backward's zero-fill on a side stream during the forward pass.
+# Off by default: with the backward directly behind the forward it is SLOWER than the in-stream zero-fill -> scatter pair
+# under programmatic dependent launch (C2 step 19.3 -> 21.4 us, profiles/r1_sweep_rejected_early_zero_fill.jsonl: the
+# cross-stream fork / join costs more than the 4.9 us fill it hides); it can only pay when other work separates the two.
+EARLY_ZERO_FILL = __import__("os").environ.get("MSDA_EARLY_ZERO_FILL", "0") == "1"
+
 _DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16, torch.float64: _capi.F64}
 
 
@@ -145,31 +151,93 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     return out
 
 
+class BackwardZeroFill:
+    """Handle of an early zero-fill of backward's accumulation buffer (``begin_backward_zero_fill``)."""
+
+    __slots__ = ("buffer", "event", "shape", "dtype")
+
+    def __init__(self, buffer, event, shape, dtype):
+        self.buffer, self.event, self.shape, self.dtype = buffer, event, shape, dtype
+
+
+_side_streams = {}
+
+
+def _side_stream(device):
+    key = device.index if device.index is not None else torch.cuda.current_device()
+    s = _side_streams.get(key)
+    if s is None:
+        s = _side_streams[key] = torch.cuda.Stream(device=device)
+    return s
+
+
+def begin_backward_zero_fill(value):
+    """Enqueue the zero-fill that ``ms_deform_attn_backward`` starts with -- grad_value (fp32 / fp64) or its fp32 accumulation
+    image (bf16 / fp16) -- on a side stream NOW, so that it overlaps whatever runs between this call and the backward pass
+    (at least the forward kernel; in a training step the rest of the network).  Pass the handle as ``prezeroed=`` to
+    ``ms_deform_attn_backward``, which waits for the fill and skips its own (C ABI: msda_zero_fill + MSDA_BWD_PREZEROED).
+    The reference allocates and zero-fills inside the backward op (ms_deform_attn_cuda.cu:121).  Works under CUDA-graph
+    capture (the side stream forks from and joins the capturing stream) provided the backward call is captured too."""
+    if not value.is_cuda:
+        raise RuntimeError("value must be a CUDA tensor")
+    dev = value.device
+    acc_dtype = value.dtype if value.dtype in (torch.float32, torch.float64) else torch.float32
+    side = _side_stream(dev)
+    side.wait_stream(torch.cuda.current_stream(dev))
+    with torch.cuda.stream(side):
+        buf = torch.empty(value.shape, dtype=acc_dtype, device=dev)
+        if buf.numel():
+            rc = _capi.lib().msda_zero_fill(buf.data_ptr(), buf.numel() * buf.element_size(), side.cuda_stream)
+            if rc != 0:
+                raise RuntimeError("msda_zero_fill failed: " + _capi.last_error())
+        ev = torch.cuda.Event()
+        ev.record(side)
+    return BackwardZeroFill(buf, ev, tuple(value.shape), value.dtype)
+
+
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step=64, grads=None):
+                            im2col_step=64, grads=None, prezeroed=None):
     """CUDA backward -> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:83-153).
 
-    ``grads`` (optional): three caller-provided result buffers shaped like value / sampling_loc / attn_weight."""
+    ``grads`` (optional): three caller-provided result buffers shaped like value / sampling_loc / attn_weight.
+    ``prezeroed`` (optional): handle from ``begin_backward_zero_fill(value)``; its buffer becomes grad_value (fp32 / fp64) or
+    the accumulation workspace (16-bit types) and the library's own zero-fill is skipped."""
     dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
                           extra=(("grad_output", grad_output),))
     if grad_output.numel() != dims.batch * dims.num_query * dims.num_heads * dims.channels:
         raise RuntimeError(f"grad_output {tuple(grad_output.shape)} does not match the forward output")
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
-    if grads is None:
-        grad_value, grad_loc, grad_attn = torch.empty_like(value), torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
-    else:
-        grad_value = _check_out(grads[0], value.shape, value, "grads[0]")
-        grad_loc = _check_out(grads[1], sampling_loc.shape, value, "grads[1]")
-        grad_attn = _check_out(grads[2], attn_weight.shape, value, "grads[2]")
     L = _capi.lib()
     dt = _DTYPES[value.dtype]
     ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
-    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
+    flags, pre_gv, ws = 0, None, None
+    if prezeroed is not None:
+        if prezeroed.shape != tuple(value.shape) or prezeroed.dtype != value.dtype or prezeroed.buffer.device != value.device:
+            raise RuntimeError("prezeroed handle was made for a different value tensor")
+        cur = torch.cuda.current_stream(value.device)
+        cur.wait_event(prezeroed.event)
+        prezeroed.buffer.record_stream(cur)  # allocated on the side stream, used (and possibly freed) on this one
+        flags = _capi.BWD_PREZEROED
+        if ws_bytes:
+            ws = prezeroed.buffer
+        else:
+            pre_gv = prezeroed.buffer
+    if grads is None:
+        grad_value = pre_gv if pre_gv is not None else torch.empty_like(value)
+        grad_loc, grad_attn = torch.empty_like(sampling_loc), torch.empty_like(attn_weight)
+    else:
+        if pre_gv is not None:
+            raise RuntimeError("grads= and prezeroed= both name a grad_value buffer")
+        grad_value = _check_out(grads[0], value.shape, value, "grads[0]")
+        grad_loc = _check_out(grads[1], sampling_loc.shape, value, "grads[1]")
+        grad_attn = _check_out(grads[2], attn_weight.shape, value, "grads[2]")
+    if ws is None and ws_bytes:
+        ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
     with _on_device(value) as stream:
         rc = L.msda_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc),
                              _ptr(attn_weight), _ptr(grad_value), _ptr(grad_loc), _ptr(grad_attn),
-                             _ptr(ws) if ws is not None else None, ws_bytes, ctypes.byref(dims), dt, 0,
+                             _ptr(ws) if ws is not None else None, ws_bytes, ctypes.byref(dims), dt, flags,
                              stream)
     if rc != 0:
         raise RuntimeError("msda_backward failed: " + _capi.last_error())
@@ -299,6 +367,12 @@ class MSDeformAttnFunction(Function):
     def forward(ctx, value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
                 im2col_step):
         ctx.im2col_step = im2col_step
+        # the backward's zero-fill starts now, on a side stream, when a backward can follow (knob: EARLY_ZERO_FILL); not
+        # under CUDA-graph capture, where the side stream could stay unjoined if the backward is not captured
+        ctx.prezeroed = None
+        if (EARLY_ZERO_FILL and value.is_cuda and any(ctx.needs_input_grad) and value.numel()
+                and not torch.cuda.is_current_stream_capturing()):
+            ctx.prezeroed = begin_backward_zero_fill(value)
         output = torch.ops.alonet_custom.ms_deform_attn_forward(
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
             ctx.im2col_step)
@@ -310,6 +384,12 @@ class MSDeformAttnFunction(Function):
     @once_differentiable
     def backward(ctx, grad_output):
         value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights = ctx.saved_tensors
+        if ctx.prezeroed is not None:
+            pre, ctx.prezeroed = ctx.prezeroed, None
+            grad_value, grad_sampling_loc, grad_attn_weight = ms_deform_attn_backward(
+                value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
+                grad_output.contiguous(), ctx.im2col_step, prezeroed=pre)
+            return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
         grad_value, grad_sampling_loc, grad_attn_weight = torch.ops.alonet_custom.ms_deform_attn_backward(
             value, value_spatial_shapes, value_level_start_index, sampling_locations, attention_weights,
             grad_output.contiguous(), ctx.im2col_step)

@@ -82,12 +82,22 @@ size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
  * None of the three gradient tensors needs initialising: grad_value is zero-filled by the library,
  * grad_sampling_loc and grad_attn_weight are written in full.
  * `workspace` : device scratch of at least msda_backward_workspace_bytes() bytes (may be NULL when 0).
- * `flags`     : reserved, pass 0.
+ * `flags`     : 0, or MSDA_BWD_PREZEROED: the caller has already zero-filled the accumulation buffer (grad_value for
+ *               MSDA_F32 / MSDA_F64, `workspace` for the 16-bit types) in stream order before this call -- e.g. with
+ *               msda_zero_fill() on a side stream while the forward pass ran; the library then skips its own fill.
  */
+#define MSDA_BWD_PREZEROED 1
 int msda_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
                   const int32_t* level_start_index, const void* sampling_loc, const void* attn_weight,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                   size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream);
+
+/*
+ * The library's zero-fill (the first of the two kernels of msda_backward) as a call of its own, so that a caller can
+ * enqueue it early on another stream (see MSDA_BWD_PREZEROED).  The reference zero-fills inside the op
+ * (`at::zeros_like`, ms_deform_attn_cuda.cu:121).
+ */
+int msda_zero_fill(void* ptr, size_t bytes, void* stream);
 
 /*
  * Host-buffer forward for callers without a device allocator (the TensorRT-plugin-style consumer,

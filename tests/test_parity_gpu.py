@@ -447,3 +447,59 @@ def test_more_than_2e31_elements_uses_64bit_indexing(cuda_device):
     assert torch.equal(gl[-1:], gl1) and torch.equal(ga[-1:], ga1)
     assert torch.allclose(gv[-1:], gv1, rtol=1e-5, atol=1e-6)   # atomics: order of accumulation may differ
     assert not gv[:-1].isnan().any()
+
+
+# ------------------------------------------------------------------ early zero-fill (MSDA_BWD_PREZEROED)
+
+@pytest.mark.parametrize("dtype", [torch.float32, torch.float64, torch.bfloat16])
+def test_backward_with_early_zero_fill(cuda_device, dtype):
+    """begin_backward_zero_fill on a side stream + prezeroed= backward gives the gradients of the in-order path."""
+    from aloception_oss_b200.synthetic import Workload, torch_inputs
+
+    w = Workload("ezf", 2, ((20, 27), (10, 14), (5, 7), (3, 4)), 50, M=8, P=4, D=32)
+    x = {k: v.to(cuda_device) for k, v in torch_inputs(w, seed=31, loc_mode="wide", dtype=dtype).items()}
+    args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"], x["grad_out"])
+    want = msda.ms_deform_attn_backward(*args)
+    poison = torch.full((1 << 22,), float("nan"), device=cuda_device)  # the next allocations reuse dirty memory
+    del poison
+    h = msda.begin_backward_zero_fill(x["value"])
+    out = msda.ms_deform_attn_forward(*args[:5])
+    got = msda.ms_deform_attn_backward(*args, prezeroed=h)
+    torch.cuda.synchronize()
+    assert torch.equal(out, msda.ms_deform_attn_forward(*args[:5]))
+    tol = dict(rtol=2e-2, atol=1e-4) if dtype == torch.bfloat16 else dict(rtol=1e-4, atol=1e-7)
+    for a, b in zip(got, want):
+        assert a.dtype == dtype and torch.allclose(a.double(), b.double(), **tol)
+    with pytest.raises(RuntimeError, match="different value tensor"):
+        msda.ms_deform_attn_backward(*args, prezeroed=msda.begin_backward_zero_fill(x["value"][:1]))
+
+
+def test_autograd_function_uses_the_early_zero_fill(cuda_device):
+    from aloception_oss_b200 import functions
+    from aloception_oss_b200.synthetic import Workload, torch_inputs
+
+    w = Workload("ezf2", 2, ((12, 16), (6, 8)), 33, M=8, P=4, D=32)
+    x = {k: v.to(cuda_device) for k, v in torch_inputs(w, seed=32, loc_mode="wide").items()}
+    grads = {}
+    default = functions.EARLY_ZERO_FILL
+    for flag in (True, False):
+        functions.EARLY_ZERO_FILL = flag
+        try:
+            v, loc, attn = (x[k].clone().requires_grad_(True) for k in ("value", "loc", "attn"))
+            n0 = _capi.kernel_launch_count()
+            out = msda.MSDeformAttnFunction.apply(v, x["shapes"], x["start"], loc, attn, 64)
+            if flag:
+                assert _capi.kernel_launch_count() == n0 + 2  # zero-fill (side stream) + forward
+            out.backward(x["grad_out"])
+            torch.cuda.synchronize()
+            assert _capi.kernel_launch_count() == n0 + 3
+            grads[flag] = (v.grad, loc.grad, attn.grad)
+        finally:
+            functions.EARLY_ZERO_FILL = default
+    for a, b in zip(grads[True], grads[False]):
+        assert torch.allclose(a, b, rtol=1e-4, atol=1e-7)
+    # forward-only under no_grad launches nothing extra
+    n0 = _capi.kernel_launch_count()
+    with torch.no_grad():
+        msda.MSDeformAttnFunction.apply(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+    assert _capi.kernel_launch_count() == n0 + 1
