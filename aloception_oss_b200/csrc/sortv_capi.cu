@@ -19,7 +19,7 @@ namespace {
 
 thread_local char g_err[256] = "";
 std::atomic<uint64_t> g_launches{0};
-std::atomic<int> g_variant{0};  // 0 = default (balanced tile kernel for m = 24), 1 = register kernels, 2 = generic kernel, 3 = unbalanced tile kernel
+std::atomic<int> g_variant{0};  // 0 = default (balanced tile kernel for m = 24), 1 = register kernels, 2 = generic kernel, 3 = unbalanced tile kernel, 4 = balanced tile kernel without the sorted-order fast path
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -197,7 +197,7 @@ __device__ __forceinline__ uint32_t sv_smem_u32(const void* p) { return (uint32_
 template <bool BAL>
 __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restrict__ vertices, const uint8_t* __restrict__ mask,
                                                            const int32_t* __restrict__ num_valid, int32_t* __restrict__ idx,
-                                                           long long total) {
+                                                           long long total, bool g_fast_order) {
   constexpr int M = 24;
   // 24 576 B: staged vertices; then the columns s_slot[kSlots + 1][kTile] (18 432 B; column p = candidates (x, y, q, index)
   // of the polygon at sorted position p, row kSlots = (vertex 0, its q, c | rounds << 8)); then the indices (4 608 B)
@@ -335,27 +335,64 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
   s_owner[position] = fast ? t : -1;
   __syncthreads();
 
-  // ---- phase B: the selection rounds over column t
+  // ---- phase B: the order of column t.
+  // Fast path: when `before` restricted to this polygon's candidates is a strict total order -- irreflexive (it is not for
+  // y = -inf: inf - inf defeats the coincidence test), every pair ordered one way exactly, the in-degrees a permutation of
+  // 0..c-1 (a tournament with that score sequence is transitive) -- every candidate comes before the start value and there
+  // is one round per candidate, the reference's rounds ("smallest
+  // candidate after the previous one", each a min-scan under that order) return the candidates in sorted order: idx[r] =
+  // the candidate with in-degree r.  That takes c (c - 1) / 2 joint evaluations of before(a, b) / before(b, a) -- they
+  // share the coincidence test, the sign classes and d = q_a - q_b (q_b - q_a = -d exactly) -- instead of 2 c^2 single ones.
+  // Anything else (coincident or zero-y vertices, near-equal quotients that break antisymmetry, more rounds than
+  // candidates) runs the rounds themselves.  Same comparator values either way, so the indices are identical.
   {
     const int owner = s_owner[t];
     if (owner >= 0) {
       const float4 h = s_slot[kSlots][t];
       const int cc = __float_as_int(h.w) & 0xff, rounds = __float_as_int(h.w) >> 8;
       unsigned long long ord = 0;
-      float px = 0.f, py = 0.f, pq = 0.f;
-      for (int j = 0; j < rounds; ++j) {
-        float x_min = 1.f, y_min = y0, q_min = q0;
-        int take = -1;
-        for (int i = 0; i < cc; ++i) {
-          const float4 s = s_slot[i][t];
-          const bool sel = before_q(s.x, s.y, s.z, x_min, y_min, q_min) & ((j == 0) | before_q(px, py, pq, s.x, s.y, s.z));
-          x_min = sel ? s.x : x_min; y_min = sel ? s.y : y_min; q_min = sel ? s.z : q_min;
-          take = sel ? __float_as_int(s.w) : take;
+      bool total = rounds == cc && g_fast_order;
+      {
+        unsigned rankword = 0, seen = 0, onehot_a = 1u;  // in-degree of candidate a in bits [4a, 4a + 4)
+        for (int a = 0; a < cc; ++a, onehot_a <<= 4) {
+          const float4 A = s_slot[a][t];
+          total &= before_q(A.x, A.y, A.z, 1.f, y0, q0) & !before_q(A.x, A.y, A.z, A.x, A.y, A.z);
+          const bool pa = A.y > 0.f, na = A.y < 0.f;
+          unsigned onehot_b = onehot_a << 4;
+          for (int b = a + 1; b < cc; ++b, onehot_b <<= 4) {
+            const float4 B = s_slot[b][t];
+            const bool tie = lt_eps(fabsf(A.x - B.x)) & lt_eps(fabsf(B.y - A.y));
+            const bool pb = B.y > 0.f, nb = B.y < 0.f;
+            const float d = __fsub_rn(A.z, B.z), nd = -d;
+            const bool ab = !tie & ((pa & nb) | (pa & pb & gt_eps(d)) | (na & nb & lt_eps(d)));
+            const bool ba = !tie & ((pb & na) | (pb & pa & gt_eps(nd)) | (nb & na & lt_eps(nd)));
+            total &= ab != ba;
+            rankword += ab ? onehot_b : 0u;
+            rankword += ba ? onehot_a : 0u;
+          }
+          const unsigned r = (rankword >> (4 * a)) & 15u;  // final: every pair with a has been seen
+          seen |= 1u << r;
+          ord |= (unsigned long long)__float_as_int(A.w) << (5 * r);
         }
-        // nothing selected: idx[j] = 0 and the next round compares against vertex 0
-        const bool none = take < 0;
-        px = none ? h.x : x_min; py = none ? h.y : y_min; pq = none ? h.z : q_min;
-        ord |= (unsigned long long)(none ? 0 : take) << (5 * j);
+        total &= seen == (1u << cc) - 1u;
+      }
+      if (!total) {
+        ord = 0;
+        float px = 0.f, py = 0.f, pq = 0.f;
+        for (int j = 0; j < rounds; ++j) {
+          float x_min = 1.f, y_min = y0, q_min = q0;
+          int take = -1;
+          for (int i = 0; i < cc; ++i) {
+            const float4 s = s_slot[i][t];
+            const bool sel = before_q(s.x, s.y, s.z, x_min, y_min, q_min) & ((j == 0) | before_q(px, py, pq, s.x, s.y, s.z));
+            x_min = sel ? s.x : x_min; y_min = sel ? s.y : y_min; q_min = sel ? s.z : q_min;
+            take = sel ? __float_as_int(s.w) : take;
+          }
+          // nothing selected: idx[j] = 0 and the next round compares against vertex 0
+          const bool none = take < 0;
+          px = none ? h.x : x_min; py = none ? h.y : y_min; pq = none ? h.z : q_min;
+          ord |= (unsigned long long)(none ? 0 : take) << (5 * j);
+        }
       }
       s_order[owner] = ord;
     }
@@ -459,7 +496,7 @@ const char* sortv_last_error_string(void) { return g_err; }
 uint64_t sortv_kernel_launch_count(void) { return g_launches.load(); }
 
 int sortv_set_variant(int variant) {
-  if (variant < 0 || variant > 3) return fail("sortv_set_variant: unknown variant %d", variant);
+  if (variant < 0 || variant > 4) return fail("sortv_set_variant: unknown variant %d", variant);
   g_variant.store(variant);
   return 0;
 }
@@ -478,8 +515,9 @@ int sortv_sort_vertices(const float* vertices, const uint8_t* mask, const int32_
   const bool a16 = (reinterpret_cast<uintptr_t>(vertices) % 16) == 0 && (reinterpret_cast<uintptr_t>(mask) % 8) == 0;
   const bool tma_ok = a16 && (reinterpret_cast<uintptr_t>(mask) % 16) == 0 && (reinterpret_cast<uintptr_t>(num_valid) % 16) == 0 &&
                       (reinterpret_cast<uintptr_t>(idx) % 16) == 0;
-  if (m == 24 && tma_ok && g_variant == 0) sortv_tile_kernel<true><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total);
-  else if (m == 24 && tma_ok && g_variant == 3) sortv_tile_kernel<false><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total);
+  if (m == 24 && tma_ok && g_variant == 0) sortv_tile_kernel<true><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total, true);
+  else if (m == 24 && tma_ok && g_variant == 3) sortv_tile_kernel<false><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total, true);
+  else if (m == 24 && tma_ok && g_variant == 4) sortv_tile_kernel<true><<<(unsigned)blocks, kTile, 0, st>>>(vertices, mask, num_valid, idx, total, false);
   else if (m == 24 && a16 && g_variant != 2) sortv_kernel<24><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
   else if (m == 16 && a16 && g_variant != 2) sortv_kernel<16><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);
   else if (m == 32 && a16 && g_variant != 2) sortv_kernel<32><<<(unsigned)blocks, 128, 0, st>>>(vertices, mask, num_valid, idx, total);

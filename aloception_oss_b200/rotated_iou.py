@@ -92,7 +92,7 @@ def kernel_launch_count() -> int:
 
 
 def set_variant(variant: int) -> None:
-    """Test / measurement knob (include/sortv_b200.h): 0 default (balanced TMA tile kernel), 1 register kernels, 2 generic kernel, 3 unbalanced tile kernel."""
+    """Test / measurement knob (include/sortv_b200.h): 0 default (balanced TMA tile kernel), 1 register kernels, 2 generic kernel, 3 unbalanced tile kernel, 4 no sorted-order fast path."""
     if lib().sortv_set_variant(int(variant)) != 0:
         raise ValueError(last_error())
 

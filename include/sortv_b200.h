@@ -46,7 +46,8 @@ const char* sortv_last_error_string(void);
 uint64_t sortv_kernel_launch_count(void);
 /* Test / measurement knob, process-wide: 0 = default schedule (TMA-staged tile kernel for m = 24 and 16-byte aligned tensors),
  * 1 = register-resident kernels only (m = 16 / 24 / 32), 2 = generic kernel only, 3 = tile kernel without the in-CTA load
- * balancing.  All variants return identical indices. */
+ * balancing, 4 = tile kernel that always runs the reference's selection rounds (no sorted-order fast path).  All variants
+ * return identical indices. */
 int sortv_set_variant(int variant);
 
 /* Replaces sort_vertices_wrapper (sort_vert_kernel.cu:136-140; torch entry sort_vert.cpp:6-29). */

@@ -70,7 +70,7 @@ int main(void) {
   CK(cudaMemcpyAsync(dv, v, np * m * 2 * sizeof(float), cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dm, mk, np * m, cudaMemcpyHostToDevice, st));
   CK(cudaMemcpyAsync(dn, nv, np * sizeof(int32_t), cudaMemcpyHostToDevice, st));
-  for (int variant = 0; variant <= 3; ++variant) {
+  for (int variant = 0; variant <= 4; ++variant) {
     if (sortv_set_variant(variant) != 0) {
       printf("sortv_set_variant(%d): %s\n", variant, sortv_last_error_string());
       return 1;

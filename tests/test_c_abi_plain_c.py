@@ -80,5 +80,5 @@ def test_sortv_plain_c_program_matches_the_oracle(tmp_path, cuda_device):
     res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
     assert res.returncode == 0, res.stdout + res.stderr
     assert "sortv C ABI smoke: OK" in res.stdout
-    for v in range(4):
+    for v in range(5):
         assert f"variant {v}     ok" in res.stdout, res.stdout

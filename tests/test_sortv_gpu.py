@@ -89,7 +89,7 @@ def test_against_oracle(cuda_device, b, n, m, seed, snap):
     assert (idx == want).all(), f"{(idx != want).any(-1).sum()} polygons differ"
 
 
-@pytest.mark.parametrize("variant", [0, 1, 2, 3])
+@pytest.mark.parametrize("variant", [0, 1, 2, 3, 4])
 @pytest.mark.parametrize("b,n,seed,snap,p_valid", [
     (8, 1024, 30, False, 0.2), (8, 1024, 31, True, 0.2), (3, 777, 32, True, 0.3), (1, 128, 33, True, 0.25),
     (2, 4099, 34, True, 0.6),  # most polygons above 8 valid candidates: the tile kernel's direct scan
@@ -115,7 +115,7 @@ def test_non_finite_vertices(cuda_device):
     v = torch.where(r < 0.02, torch.full_like(v, float("nan")), v)
     v = torch.where((r >= 0.02) & (r < 0.04), torch.full_like(v, float("inf")), v)
     v = torch.where((r >= 0.04) & (r < 0.05), torch.full_like(v, -float("inf")), v)
-    for variant in (0, 1, 2, 3):
+    for variant in (0, 1, 2, 3, 4):
         rotated_iou.set_variant(variant)
         try:
             idx = ours(v, mask, nv, cuda_device)

@@ -111,6 +111,55 @@ def test_edge_cases():
     assert (idx == 23).all()
 
 
+# ------------------------------------------------------------------ the kernel's sorted-order fast path, modelled on the CPU
+
+def _random_polygons(b, n, seed, snap, p_valid=0.25):
+    rng = np.random.default_rng(seed)
+    v = rng.random((b, n, 24, 2), dtype=np.float32)
+    if snap:
+        v = np.round(v * 4) / 4 - 0.5
+    else:
+        v = v - v.mean(axis=2, keepdims=True)
+    mask = rng.random((b, n, 24)) < p_valid
+    return v.astype(np.float32), mask, mask.sum(-1).astype(np.int32)
+
+
+@pytest.mark.parametrize("kind", ["continuous", "quantised", "non_finite", "near_tie", "tiny_scale"])
+def test_sorted_order_fast_path_model_agrees_with_the_selection_rounds(kind, tmp_path):
+    """Whenever `before` is a strict total order on a polygon's candidates (the checks of sortv_capi.cu phase B), the sorted
+    order IS the result of the reference's rounds -- including the y = -inf case that breaks irreflexivity."""
+    import subprocess
+
+    so = str(tmp_path / "fast_model.so")
+    subprocess.run(["gcc", "-O2", "-ffp-contract=off", "-shared", "-fPIC", "-o", so,
+                    os.path.join(ROOT, "tests", "c_abi", "sortv_fast_order_model.c"), "-lm"], check=True)
+    L = ctypes.CDLL(so)
+    L.fast_order.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_int, ctypes.c_int, ctypes.c_void_p, ctypes.c_void_p]
+    v, mask, nv = _random_polygons(2, 2048, 5, snap=kind != "continuous")
+    rng = np.random.default_rng(6)
+    if kind == "non_finite":
+        r = rng.random(v.shape)
+        v = np.where(r < 0.03, np.float32("nan"), v)
+        v = np.where((r >= 0.03) & (r < 0.07), np.float32("inf"), v)
+        v = np.where((r >= 0.07) & (r < 0.11), np.float32("-inf"), v).astype(np.float32)
+    elif kind == "near_tie":
+        v = (v + (rng.random(v.shape, dtype=np.float32) - 0.5) * np.float32(4e-8)).astype(np.float32)
+    elif kind == "tiny_scale":
+        v = (v * np.float32(1e-4)).astype(np.float32)
+    want = sortv_oracle.sort_vertices(v, mask, nv).reshape(-1, 9)
+    vv, mm, nn = v.reshape(-1, 24, 2), mask.reshape(-1, 24).astype(np.uint8), nv.reshape(-1)
+    out, ap = (ctypes.c_int * 9)(), ctypes.c_int(0)
+    applied = 0
+    for p in range(vv.shape[0]):
+        vp, mp = np.ascontiguousarray(vv[p]), np.ascontiguousarray(mm[p])
+        L.fast_order(vp.ctypes.data, mp.ctypes.data, int(nn[p]), 24, out, ctypes.byref(ap))
+        if ap.value:
+            applied += 1
+            c = int(min(nn[p], 8))
+            assert list(out)[:c] == want[p, :c].tolist(), (kind, p)
+    assert applied > (2000 if kind == "continuous" else 100), applied
+
+
 # ------------------------------------------------------------------ C ABI surface (no GPU: no compute calls)
 
 HEADER = os.path.join(ROOT, "include", "sortv_b200.h")
