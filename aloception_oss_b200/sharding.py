@@ -29,6 +29,21 @@ def shard_batch(value, sampling_locations, attention_weights, rank: int, world: 
     return value[b:e], sampling_locations[b:e], attention_weights[b:e]
 
 
+def shard_polygons(vertices, mask, num_valid, rank: int, world: int):
+    """`sort_vertices` (rotated_iou): polygons are independent (sort_vert_kernel.cu:53: one loop iteration per polygon), so the
+    (b, n) grid shards like the images above.  Slices dim 0 when b >= world, else flattens to (1, b * n, ...) and slices
+    the polygon axis; returns contiguous (b', n', m, 2), (b', n', m), (b', n') for this rank and the ``[begin, end)`` range
+    in units of the sliced axis."""
+    b, n = vertices.shape[0], vertices.shape[1]
+    if b >= world:
+        lo, hi = shard_range(b, rank, world)
+        return vertices[lo:hi], mask[lo:hi], num_valid[lo:hi], (lo, hi)
+    lo, hi = shard_range(b * n, rank, world)
+    m = vertices.shape[2]
+    return (vertices.reshape(1, b * n, m, 2)[:, lo:hi].contiguous(), mask.reshape(1, b * n, m)[:, lo:hi].contiguous(),
+            num_valid.reshape(1, b * n)[:, lo:hi].contiguous(), (lo, hi))
+
+
 def broadcast_level_metadata(spatial_shapes, level_start_index, src: int = 0, group=None):
     """One broadcast of the replicated metadata from ``src``; returns the (in-place updated) tensors."""
     import torch.distributed as dist

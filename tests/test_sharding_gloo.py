@@ -49,3 +49,41 @@ def test_batch_sharding_world2_gloo():
     ret = mgr.dict()
     mp.spawn(_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
     assert dict(ret) == {0: True, 1: True}
+
+
+def _sortv_worker(rank, world, port, ret):
+    import numpy as np
+
+    from oracle import sortv_oracle
+
+    os.environ.update(MASTER_ADDR="127.0.0.1", MASTER_PORT=str(port))
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        ok = True
+        for b, n in ((5, 37), (1, 101)):  # uneven batch shards; b < world: the polygon axis is split instead
+            g = torch.Generator().manual_seed(17)
+            v = torch.round(torch.rand(b, n, 24, 2, generator=g) * 4) / 4 - 0.5
+            mask = torch.rand(b, n, 24, generator=g) < 0.25
+            nv = mask.sum(-1).int()
+            ref = torch.from_numpy(sortv_oracle.sort_vertices(v.numpy(), mask.numpy(), nv.numpy()))
+            sv, sm, sn, (lo, hi) = sharding.shard_polygons(v, mask, nv, rank, world)
+            assert sv.is_contiguous() and sm.is_contiguous() and sn.is_contiguous()
+            local = torch.from_numpy(sortv_oracle.sort_vertices(sv.numpy(), sm.numpy(), sn.numpy()))
+            if b >= world:
+                full = sharding.gather_outputs(local, b)
+            else:
+                full = sharding.gather_outputs(local[0], b * n).reshape(b, n, 9)
+            ok = ok and bool(torch.equal(full, ref))
+        ret[rank] = ok
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(120)
+def test_polygon_sharding_world2_gloo():
+    """sort_vertices shards by polygon ranges with no collective; the gather reproduces the unsharded indices."""
+    world = 2
+    mgr = mp.Manager()
+    ret = mgr.dict()
+    mp.spawn(_sortv_worker, args=(world, _free_port(), ret), nprocs=world, join=True)
+    assert dict(ret) == {0: True, 1: True}
