@@ -26,6 +26,13 @@
 #define MSDA_FWD_MIN_CTAS 6
 #endif
 
+// Register cap of the U=1 backward kernel.  56 = nine 128-thread CTAs per SM = 1 332 resident CTAs: the 1 200 CTAs of a
+// C2-sized call (N=2, 300 queries, 8 heads; one warp per unit) run as ONE wave.  At 57..64 registers only eight fit (1 184)
+// and the call takes a second, nearly empty wave (measured: backward 13.1 -> 14.7 us).
+#ifndef MSDA_BWD_MAX_REGS
+#define MSDA_BWD_MAX_REGS 56
+#endif
+
 namespace msda {
 
 // ------------------------------------------------------------------------------------------------
@@ -1126,7 +1133,7 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
 // location arithmetic differentiated in the kernel), `gref` (fp32, pre-zeroed, may be null) accumulates the gradient
 // w.r.t. the reference points with scalar reds (M*P contributions per element).
 template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? 4 : (U == 2 ? 3 : 2))
+__global__ void __maxnreg__(U == 1 ? MSDA_BWD_MAX_REGS : (U == 2 ? 80 : 128))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,

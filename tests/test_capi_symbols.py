@@ -68,3 +68,31 @@ def test_tuning_knobs_roundtrip():
         assert "unknown tuning knob" in str(e)
     else:
         raise AssertionError("unknown knob accepted")
+
+
+def test_register_budgets_of_the_default_kernels():
+    """One-wave residency of a C2-sized call (1 200 CTAs of 128 threads) needs <= 56 registers in the backward kernel (nine
+    CTAs per SM) and the forward kernel is tuned at 40; a silent increase costs a second wave (measured: backward 13.1 -> 14.7
+    us when a change took the kernel to 61).  Read from the built library with cuobjdump."""
+    import shutil
+    import subprocess
+
+    import pytest
+
+    if shutil.which("cuobjdump") is None:
+        pytest.skip("cuobjdump not on PATH")
+    _capi.build_library()
+    txt = subprocess.run(["cuobjdump", "--dump-resource-usage", _capi.LIB_PATH], capture_output=True, text=True).stdout
+    regs = {}
+    name = None
+    for line in txt.splitlines():
+        m = re.search(r"Function (\S+):", line)
+        if m:
+            name = m.group(1)
+        m = re.search(r"REG:(\d+)", line)
+        if m and name:
+            regs[name] = int(m.group(1))
+    bwd = [v for k, v in regs.items() if "msda_bwd_sg_kernelIfLi32ELi8ELi1ELb0" in k]
+    fwd = [v for k, v in regs.items() if "msda_fwd_sg_kernelIfLi32ELi8ELi1ELb0ELb1" in k]
+    assert bwd and max(bwd) <= 56, bwd
+    assert fwd and max(fwd) <= 40, fwd
