@@ -32,6 +32,9 @@
 #ifndef MSDA_BWD_MAX_REGS
 #define MSDA_BWD_MAX_REGS 56
 #endif
+#ifndef MSDA_BWD_MAX_REGS_FUSED  // the fused kernel (softmax + location arithmetic inside) spills 16 bytes at 56
+#define MSDA_BWD_MAX_REGS_FUSED 56
+#endif
 
 namespace msda {
 
@@ -1133,7 +1136,7 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
 // location arithmetic differentiated in the kernel), `gref` (fp32, pre-zeroed, may be null) accumulates the gradient
 // w.r.t. the reference points with scalar reds (M*P contributions per element).
 template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __maxnreg__(U == 1 ? MSDA_BWD_MAX_REGS : (U == 2 ? 80 : 128))
+__global__ void __maxnreg__(U == 1 ? (FUSED ? MSDA_BWD_MAX_REGS_FUSED : MSDA_BWD_MAX_REGS) : (U == 2 ? 80 : 128))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
