@@ -197,7 +197,7 @@ __device__ __forceinline__ uint32_t sv_smem_u32(const void* p) { return (uint32_
 template <bool BAL>
 __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restrict__ vertices, const uint8_t* __restrict__ mask,
                                                            const int32_t* __restrict__ num_valid, int32_t* __restrict__ idx,
-                                                           long long total, bool g_fast_order) {
+                                                           long long total, bool fast_order) {
   constexpr int M = 24;
   // 24 576 B: staged vertices; then the columns s_slot[kSlots + 1][kTile] (18 432 B; column p = candidates (x, y, q, index)
   // of the polygon at sorted position p, row kSlots = (vertex 0, its q, c | rounds << 8)); then the indices (4 608 B)
@@ -351,7 +351,7 @@ __global__ void __launch_bounds__(kTile) sortv_tile_kernel(const float* __restri
       const float4 h = s_slot[kSlots][t];
       const int cc = __float_as_int(h.w) & 0xff, rounds = __float_as_int(h.w) >> 8;
       unsigned long long ord = 0;
-      bool total = rounds == cc && g_fast_order;
+      bool total = rounds == cc && fast_order;
       {
         unsigned rankword = 0, seen = 0, onehot_a = 1u;  // in-degree of candidate a in bits [4a, 4a + 4)
         for (int a = 0; a < cc; ++a, onehot_a <<= 4) {

@@ -17,6 +17,7 @@ memory and the current stream.  There is no CPU implementation: CPU tensors rais
 from __future__ import annotations
 
 import ctypes
+import os
 
 import torch
 import torch.nn.functional as F
@@ -29,7 +30,7 @@ from . import _capi
 # Off by default: with the backward directly behind the forward it is SLOWER than the in-stream zero-fill -> scatter pair
 # under programmatic dependent launch (C2 step 19.3 -> 21.4 us, profiles/r1_sweep_rejected_early_zero_fill.jsonl: the
 # cross-stream fork / join costs more than the 4.9 us fill it hides); it can only pay when other work separates the two.
-EARLY_ZERO_FILL = __import__("os").environ.get("MSDA_EARLY_ZERO_FILL", "0") == "1"
+EARLY_ZERO_FILL = os.environ.get("MSDA_EARLY_ZERO_FILL", "0") == "1"
 
 _DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16, torch.float64: _capi.F64}
 
