@@ -1,5 +1,8 @@
-// Prototype / microbenchmark (GPU box; NOT product code, NOT YET RUN -- written at the end of round 1 when the GPU budget was
-// spent; DESIGN.md section 8 "open leads" (1)): the grad_value scatter of an ENCODER backward call, two ways.
+// Prototype / microbenchmark (GPU box; NOT product code; DESIGN.md section 8 "open leads" (1)): the grad_value scatter of an
+// ENCODER backward call, two ways.  First (and, in round 1, only) run, profiles/r1_microbench_tile_binned_scatter.jsonl: (B) is
+// CORRECT (max |A - B| = 6.7e-7 of 0.60) and issues 11 x fewer reds (9.9 M vs 108.9 M 16-byte reds), but takes 279 us against
+// 237 us for (A): with the reds gone this first version is bound by its own phases (2 CTAs = 16 warps per SM at 82 KB of
+// shared memory, five block barriers per level, 8-way conflicted staging of the grad_out rows, one thread per fallback row).
 //   (A) direct: one warp per (image, query, head) unit, 16 samples x 4 taps, every tap a 128-byte row of
 //       `red.global.add.v4.f32` -- what msda_bwd_sg_kernel does (13.6 M reds per call at N=2; bound by the SM-side red rate,
 //       5.9 clk per row);
