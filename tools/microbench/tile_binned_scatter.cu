@@ -16,17 +16,17 @@
 // Inputs follow aloception_oss_b200/synthetic.py "raster": N=2, levels 100^2/50^2/25^2/13^2, query i = pixel i, reference point
 // = pixel centre, offsets uniform +-4 pixels of each sampled level, M=8, P=4, D=32.
 //   nvcc -O3 -std=c++17 -gencode arch=compute_100a,code=sm_100a -o tile_binned_scatter tile_binned_scatter.cu && ./tile_binned_scatter
-// Prints one JSON line: microseconds of (A) and (B), reds issued by (B), max |A - B| relative to max |A|.
+// Prints one JSON line per configuration of (B) -- tile edge 16 / 8, window capacity, cooperative staging of the grad_out rows
+// (the variants after the first were added AFTER the measured run and have only been compiled): microseconds of (A) and (B),
+// reds issued by (B), max |A - B| relative to max |A|.
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
 #include <cuda_runtime.h>
 
 constexpr int L = 4, M = 8, P = 4, D = 32;
-constexpr int T = 16;          // tile edge (queries)
-constexpr int TQ = T * T;      // 256 queries = 256 threads
-constexpr int MAXB = 2048;     // bins (destination rows) a window may hold
-constexpr int NREC = TQ * P * 4;
+// Tile edge T (T*T queries = T*T threads per CTA), MAXB = bins (destination rows) a window may hold, COOP = stage the grad_out
+// rows with coalesced cooperative loads (8 lanes per row) instead of one thread per row: template parameters of k_binned.
 
 struct Levels {
   int H[L], W[L], start[L];
@@ -115,9 +115,12 @@ struct TileMap {
   int tiles_x[L];
 };
 
-__global__ void __launch_bounds__(TQ) k_binned(const float* __restrict__ loc, const float* __restrict__ attn,
-                                               const float* __restrict__ go, float* __restrict__ gv, Levels lv, TileMap tm,
-                                               int N, int halo, unsigned long long* __restrict__ red_count) {
+template <int T, int MAXB, bool COOP>
+__global__ void __launch_bounds__(T * T) k_binned(const float* __restrict__ loc, const float* __restrict__ attn,
+                                                 const float* __restrict__ go, float* __restrict__ gv, Levels lv, TileMap tm,
+                                                 int N, int halo, unsigned long long* __restrict__ red_count) {
+  constexpr int TQ = T * T, NREC = TQ * P * 4;
+  static_assert(TQ % 32 == 0 && MAXB % TQ == 0, "tile must be whole warps; MAXB a multiple of the CTA size");
   extern __shared__ __align__(16) unsigned char smem[];
   float4* g_s = reinterpret_cast<float4*>(smem);                       // [TQ][8] float4 = 32 KB: grad_out rows of the tile
   int2* rec = reinterpret_cast<int2*>(smem + TQ * D * 4);               // [NREC] (query, weight bits) = 32 KB
@@ -136,7 +139,18 @@ __global__ void __launch_bounds__(TQ) k_binned(const float* __restrict__ loc, co
   const long long q = lv.start[lq] + (long long)qy * Wq + qx;
   const long long unit = (((long long)n * lv.S + q) * M + m);
   // the tile's grad_out rows
-  {
+  if constexpr (COOP) {  // 8 lanes per row: 128-byte coalesced loads, conflict-free 512-byte stores per warp instruction
+    for (int i = t; i < TQ * 8; i += TQ) {
+      const int r = i >> 3, c = i & 7;
+      const int rx = tx * T + (r % T), ry = ty * T + (r / T);
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (rx < Wq && ry < Hq) {
+        const long long ru = (((long long)n * lv.S + lv.start[lq] + (long long)ry * Wq + rx) * M + m);
+        v = *(reinterpret_cast<const float4*>(go + ru * D) + c);
+      }
+      g_s[i] = v;
+    }
+  } else {
     const float4* src = reinterpret_cast<const float4*>(go + unit * D);
 #pragma unroll
     for (int k = 0; k < 8; ++k) g_s[t * 8 + k] = have ? src[k] : make_float4(0.f, 0.f, 0.f, 0.f);
@@ -259,7 +273,56 @@ __global__ void k_maxdiff(const float* a, const float* b, long long n, float* ou
   atomicMax(reinterpret_cast<int*>(out) + 1, __float_as_int(mx));
 }
 
+
 #define CK(x) do { cudaError_t e_ = (x); if (e_ != cudaSuccess) { printf("CUDA error %s at line %d\n", cudaGetErrorString(e_), __LINE__); return 1; } } while (0)
+
+struct Ctx {
+  float *loc, *attn, *go, *gvA, *gvB, *diff;
+  unsigned long long* reds;
+  Levels lv;
+  int N, halo;
+  float offs;
+  long long n_samp, n_val;
+  float usA;
+  cudaEvent_t e0, e1;
+};
+
+template <int T, int MAXB, bool COOP>
+int run_binned(const Ctx& c) {
+  constexpr int TQ = T * T, NREC = TQ * P * 4;
+  TileMap tm;
+  tm.first_tile[0] = 0;
+  for (int l = 0; l < L; ++l) {
+    tm.tiles_x[l] = (c.lv.W[l] + T - 1) / T;
+    tm.first_tile[l + 1] = tm.first_tile[l] + tm.tiles_x[l] * ((c.lv.H[l] + T - 1) / T);
+  }
+  const size_t smem = (size_t)TQ * D * 4 + (size_t)NREC * 8 + (size_t)(2 * MAXB + 1) * 4;
+  CK(cudaFuncSetAttribute(k_binned<T, MAXB, COOP>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  const dim3 gridB(tm.first_tile[L], M, c.N);
+  float usB = 1e30f, ms;
+  unsigned long long h = 0;
+  for (int rep = 0; rep < 5; ++rep) {
+    CK(cudaMemsetAsync(c.gvB, 0, c.n_val * sizeof(float)));
+    CK(cudaMemsetAsync(c.reds, 0, sizeof(unsigned long long)));
+    CK(cudaEventRecord(c.e0));
+    k_binned<T, MAXB, COOP><<<gridB, TQ, smem>>>(c.loc, c.attn, c.go, c.gvB, c.lv, tm, c.N, c.halo, rep == 0 ? c.reds : nullptr);
+    CK(cudaEventRecord(c.e1));
+    CK(cudaEventSynchronize(c.e1));
+    CK(cudaEventElapsedTime(&ms, c.e0, c.e1));
+    if (rep > 0) usB = ms * 1e3f < usB ? ms * 1e3f : usB;  // rep 0 carries the red counter
+    if (rep == 0) CK(cudaMemcpy(&h, c.reds, sizeof(h), cudaMemcpyDeviceToHost));
+  }
+  CK(cudaMemset(c.diff, 0, 2 * sizeof(float)));
+  k_maxdiff<<<148 * 4, 256>>>(c.gvA, c.gvB, c.n_val, c.diff);
+  float hd[2];
+  CK(cudaMemcpy(hd, c.diff, sizeof(hd), cudaMemcpyDeviceToHost));
+  printf("{\"tile\": %d, \"max_bins\": %d, \"coop_staging\": %s, \"smem_bytes\": %zu, \"reds_v4_binned\": %llu, \"reds_v4_direct\": %lld, "
+         "\"halo\": %d, \"offset_px\": %.1f, \"direct_us\": %.1f, \"binned_us\": %.1f, \"speedup\": %.2f, \"max_abs_diff\": %.3e, "
+         "\"max_abs\": %.3e, \"ok\": %s}\n",
+         T, MAXB, COOP ? "true" : "false", smem, h, c.n_samp * 4 * 8, c.halo, c.offs, c.usA, usB, c.usA / usB, hd[0], hd[1],
+         hd[0] <= 1e-4f * hd[1] ? "true" : "false");
+  return 0;
+}
 
 int main(int argc, char** argv) {
   const int N = 2;
@@ -269,12 +332,6 @@ int main(int argc, char** argv) {
   const int hw[L] = {100, 50, 25, 13};
   lv.S = 0;
   for (int l = 0; l < L; ++l) { lv.H[l] = lv.W[l] = hw[l]; lv.start[l] = lv.S; lv.S += hw[l] * hw[l]; }
-  TileMap tm;
-  tm.first_tile[0] = 0;
-  for (int l = 0; l < L; ++l) {
-    tm.tiles_x[l] = (lv.W[l] + T - 1) / T;
-    tm.first_tile[l + 1] = tm.first_tile[l] + tm.tiles_x[l] * ((lv.H[l] + T - 1) / T);
-  }
   const long long n_samp = (long long)N * lv.S * M * L * P, n_val = (long long)N * lv.S * M * D;
   float *loc, *attn, *go, *gvA, *gvB, *diff;
   unsigned long long* reds;
@@ -287,14 +344,11 @@ int main(int argc, char** argv) {
   CK(cudaMalloc(&reds, sizeof(unsigned long long)));
   k_init<<<148 * 8, 256>>>(loc, attn, go, lv, N, offs);
   CK(cudaGetLastError());
-  const size_t smem = (size_t)TQ * D * 4 + (size_t)NREC * 8 + (size_t)(2 * MAXB + 1) * 4;
-  CK(cudaFuncSetAttribute(k_binned, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   const long long units = (long long)N * lv.S * M;
-  const dim3 gridB(tm.first_tile[L], M, N);
   cudaEvent_t e0, e1;
   CK(cudaEventCreate(&e0));
   CK(cudaEventCreate(&e1));
-  float usA = 1e30f, usB = 1e30f;
+  float usA = 1e30f;
   for (int rep = 0; rep < 5; ++rep) {
     CK(cudaMemsetAsync(gvA, 0, n_val * sizeof(float)));
     CK(cudaEventRecord(e0));
@@ -304,25 +358,12 @@ int main(int argc, char** argv) {
     float ms;
     CK(cudaEventElapsedTime(&ms, e0, e1));
     usA = ms * 1e3f < usA ? ms * 1e3f : usA;
-    CK(cudaMemsetAsync(gvB, 0, n_val * sizeof(float)));
-    CK(cudaMemsetAsync(reds, 0, sizeof(unsigned long long)));
-    CK(cudaEventRecord(e0));
-    k_binned<<<gridB, TQ, smem>>>(loc, attn, go, gvB, lv, tm, N, halo, rep == 0 ? reds : nullptr);
-    CK(cudaEventRecord(e1));
-    CK(cudaEventSynchronize(e1));
-    CK(cudaEventElapsedTime(&ms, e0, e1));
-    if (rep > 0) usB = ms * 1e3f < usB ? ms * 1e3f : usB;  // rep 0 carries the red counter
-    if (rep == 0) {
-      unsigned long long h = 0;
-      CK(cudaMemcpy(&h, reds, sizeof(h), cudaMemcpyDeviceToHost));
-      printf("{\"reds_v4_binned\": %llu, \"reds_v4_direct\": %lld, ", h, n_samp * 4 * 8);
-    }
   }
-  CK(cudaMemset(diff, 0, 2 * sizeof(float)));
-  k_maxdiff<<<148 * 4, 256>>>(gvA, gvB, n_val, diff);
-  float hd[2];
-  CK(cudaMemcpy(hd, diff, sizeof(hd), cudaMemcpyDeviceToHost));
-  printf("\"halo\": %d, \"offset_px\": %.1f, \"direct_us\": %.1f, \"binned_us\": %.1f, \"speedup\": %.2f, \"max_abs_diff\": %.3e, \"max_abs\": %.3e, \"ok\": %s}\n",
-         halo, offs, usA, usB, usA / usB, hd[0], hd[1], hd[0] <= 1e-4f * hd[1] ? "true" : "false");
+  Ctx cx{loc, attn, go, gvA, gvB, diff, reds, lv, N, halo, offs, n_samp, n_val, usA, e0, e1};
+  if (run_binned<16, 2048, false>(cx)) return 1;  // the configuration of the first run
+  if (run_binned<16, 2048, true>(cx)) return 1;
+  if (run_binned<16, 1024, true>(cx)) return 1;   // finer level of coarse-query tiles goes direct; 66 KB
+  if (run_binned<8, 512, true>(cx)) return 1;     // 20 KB, 64-thread CTAs: more CTAs per SM, 4.5 x fewer reds instead of 11 x
+  if (run_binned<8, 1024, true>(cx)) return 1;
   return 0;
 }
