@@ -96,3 +96,27 @@ def test_register_budgets_of_the_default_kernels():
     fwd = [v for k, v in regs.items() if "msda_fwd_sg_kernelIfLi32ELi8ELi1ELb0ELb1" in k]
     assert bwd and max(bwd) <= 56, bwd
     assert fwd and max(fwd) <= 40, fwd
+
+
+def test_prezeroed_flag_and_zero_fill_validation():
+    """MSDA_BWD_PREZEROED is the only defined flag bit; msda_zero_fill validates before touching the device."""
+    lib = _capi.lib()
+    dims = _capi.MsdaDims(1, 4, 1, 32, 1, 1, 1)
+    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32, 2, None)
+    assert rc != 0 and "unknown flags" in _capi.last_error()
+    # the flag itself passes flag validation (the call then fails on the NULL tensors, not on the flag)
+    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32,
+                           _capi.BWD_PREZEROED, None)
+    assert rc != 0 and "unknown flags" not in _capi.last_error()
+    assert lib.msda_zero_fill(None, 0, None) == 0
+    assert lib.msda_zero_fill(None, 64, None) != 0 and "NULL" in _capi.last_error()
+
+
+def test_early_zero_fill_rejects_cpu_tensors():
+    import pytest
+    import torch
+
+    import aloception_oss_b200 as msda
+
+    with pytest.raises(RuntimeError, match="CUDA tensor"):
+        msda.begin_backward_zero_fill(torch.zeros(1, 4, 1, 32))
