@@ -124,7 +124,7 @@ def _random_polygons(b, n, seed, snap, p_valid=0.25):
     return v.astype(np.float32), mask, mask.sum(-1).astype(np.int32)
 
 
-@pytest.mark.parametrize("kind", ["continuous", "quantised", "non_finite", "near_tie", "tiny_scale"])
+@pytest.mark.parametrize("kind", ["continuous", "quantised", "non_finite", "near_tie", "tiny_scale", "special_values"])
 def test_sorted_order_fast_path_model_agrees_with_the_selection_rounds(kind, tmp_path):
     """Whenever `before` is a strict total order on a polygon's candidates (the checks of sortv_capi.cu phase B), the sorted
     order IS the result of the reference's rounds -- including the y = -inf case that breaks irreflexivity."""
@@ -146,6 +146,13 @@ def test_sorted_order_fast_path_model_agrees_with_the_selection_rounds(kind, tmp
         v = (v + (rng.random(v.shape, dtype=np.float32) - 0.5) * np.float32(4e-8)).astype(np.float32)
     elif kind == "tiny_scale":
         v = (v * np.float32(1e-4)).astype(np.float32)
+    elif kind == "special_values":  # signed zeros, denormals, the epsilon's neighbours, overflowing squares, Inf, NaN
+        special = np.array([0.0, -0.0, 1e-45, -1e-45, 1e-40, -1e-40, 1e-30, -1e-30, 1e-8, -1e-8, 9.9999999e-9, 1.0000001e-8,
+                            1e-4, -1e-4, 0.25, -0.25, 0.5, -0.5, 1.0, -1.0, 0.99999994, 1.0000001, 1e18, -1e18, 1e19, -1e19,
+                            1.8e19, 2e19, 1e20, -1e20, 3e38, -3e38, np.inf, -np.inf, np.nan], dtype=np.float32)
+        v = special[rng.integers(0, len(special), size=(2, 8192, 24, 2))]
+        mask = rng.random((2, 8192, 24)) < 0.2
+        nv = mask.sum(-1).astype(np.int32)
     want = sortv_oracle.sort_vertices(v, mask, nv).reshape(-1, 9)
     vv, mm, nn = v.reshape(-1, 24, 2), mask.reshape(-1, 24).astype(np.uint8), nv.reshape(-1)
     out, ap = (ctypes.c_int * 9)(), ctypes.c_int(0)
@@ -157,7 +164,7 @@ def test_sorted_order_fast_path_model_agrees_with_the_selection_rounds(kind, tmp
             applied += 1
             c = int(min(nn[p], 8))
             assert list(out)[:c] == want[p, :c].tolist(), (kind, p)
-    assert applied > (2000 if kind == "continuous" else 100), applied
+    assert applied > (2000 if kind == "continuous" else 100), applied  # the fast path really was exercised
 
 
 # ------------------------------------------------------------------ C ABI surface (no GPU: no compute calls)
