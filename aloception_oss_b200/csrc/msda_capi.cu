@@ -15,12 +15,13 @@
 #include <type_traits>
 
 #include "msda_kernels.cuh"
+#include "msda_bwd_tile.cuh"
 
 namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -398,6 +399,63 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   return 0;
 }
 
+// Tile-binned backward (msda_bwd_tile.cuh): fp32, D = 32, P = 4.  knob "bwd_tile_mode": 0 = auto, 1 = off, 2 = on.
+// Auto is OFF: measured on the B200 (profiles/r2_bwd_tile_*.jsonl, r2_ncu_bwd_tile.md) the kernel issues 5 x fewer reds and
+// fetches each window row once per tile, but it is instruction-bound (13 warp instructions per tap against 11 for the
+// unit-ordered kernel, which is bound by the red rate instead): ENC 331 us vs 266 us, C5ENC 497 vs 453 us.  It stays as a
+// tested schedule of the same function (any sampling locations, any Lq) for callers that want fewer atomics.
+constexpr int kTileTPQ = 2, kTileMaxB = 2048;
+
+bool bwd_tile_shape_ok(const msda_dims& d) {
+  return d.channels == 32 && d.num_point == 4 && d.num_levels >= 1 && d.num_levels <= 16 && d.spatial_size <= (1 << 19) &&
+         (long long)d.spatial_size * d.num_heads * d.channels < (1LL << 29) &&
+         d.num_query >= 1 && (long long)d.num_query * d.num_heads * d.num_levels * d.num_point < (1LL << 31) &&
+         d.batch <= 65535;
+}
+
+bool bwd_tile_auto(const msda_dims& d) {
+  (void)d;
+  return false;
+}
+
+int launch_bwd_tile(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                    const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st) {
+  using Cfg = msda::BwdTileCfg<32, 4, kTileTPQ, kTileMaxB>;
+  auto kern = msda::msda_bwd_tile_kernel<32, 4, kTileTPQ, kTileMaxB>;
+  static std::atomic<int> smem_set[64];
+  int dev_ = 0;
+  cudaGetDevice(&dev_);
+  std::atomic<int>& slot = smem_set[dev_ & 63];
+  if (!slot.load(std::memory_order_relaxed)) {
+    const cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM_BYTES);
+    if (ae != cudaSuccess) return fail("msda_backward(tile): cudaFuncSetAttribute(%zu B): %s", (size_t)Cfg::SMEM_BYTES, cudaGetErrorString(ae));
+    slot.store(1, std::memory_order_relaxed);
+  }
+  int per_sm = g_bwd_tile_ctas.load(std::memory_order_relaxed);
+  if (per_sm <= 0 || per_sm > 2) per_sm = 2;
+  // upper bound of the work items (the level shapes live in device memory): ceil-tiles of every level + tail tiles
+  const long long max_tiles = (long long)(d.num_query + 255) / 256 + (long long)d.spatial_size / 256 + 2LL * d.num_levels * 64 + 4;
+  long long ctas = (long long)sm_count() * per_sm;
+  const long long max_items = max_tiles * d.batch * d.num_heads;
+  if (ctas > max_items) ctas = max_items;
+  cudaLaunchConfig_t cfg{};
+  cfg.gridDim = dim3((unsigned)ctas);
+  cfg.blockDim = dim3((unsigned)Cfg::THREADS);
+  cfg.dynamicSmemBytes = Cfg::SMEM_BYTES;
+  cfg.stream = st;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+  const size_t fill_bytes = sizeof(float) * (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  const bool pdl = !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20) && !t_prezeroed;
+  attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  const cudaError_t e = cudaLaunchKernelEx(&cfg, kern, (const float*)go, (const float*)value, shapes, start, (const float*)loc,
+                                           (const float*)attn, gv, (float*)gloc, (float*)gattn, d.batch, d.spatial_size,
+                                           d.num_heads, d.num_levels, d.num_query);
+  return check_pdl_launch(e, "msda_backward(tile)");
+}
+
 template <typename T>
 int backward_typed(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
                    const void* attn, void* grad_value, void* gloc, void* gattn, void* workspace, const msda_dims& d,
@@ -410,7 +468,16 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
     if (int rc = zero_fill(acc, n_value * sizeof(A), st)) return rc;
   if (units > 0 && d.channels > 0 && d.num_levels * d.num_point > 0) {
     bool done = false;
-    if constexpr (!std::is_same<T, double>::value) {
+    if constexpr (std::is_same<T, float>::value) {
+      const int tm = g_bwd_tile_mode.load(std::memory_order_relaxed);
+      if (tm != 1 && bwd_tile_shape_ok(d) && (tm == 2 || bwd_tile_auto(d)) && !g_force_generic.load(std::memory_order_relaxed) &&
+          aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) && aligned(loc, 16) && aligned(attn, 16) &&
+          aligned(gloc, 16) && aligned(gattn, 16)) {
+        if (int rc = launch_bwd_tile(go, value, shapes, start, loc, attn, (float*)acc, gloc, gattn, d, st)) return rc;
+        done = true;
+      }
+    }
+    if constexpr (!std::is_same<T, double>::value) if (!done) {
       const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) &&
                           aligned(loc, 2 * sizeof(T)) && aligned(gloc, 2 * sizeof(T)) && aligned(attn, sizeof(T));
       if (vec_ok) {
@@ -562,6 +629,8 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "staged_kb")) return &g_staged_kb;
   if (!strcmp(name, "staged_variant")) return &g_staged_variant;
   if (!strcmp(name, "staged_warps")) return &g_staged_warps;
+  if (!strcmp(name, "bwd_tile_mode")) return &g_bwd_tile_mode;
+  if (!strcmp(name, "bwd_tile_ctas")) return &g_bwd_tile_ctas;
   return nullptr;
 }
 

@@ -114,22 +114,50 @@ class ClockSampler:
 # ------------------------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the reference's CPU implementation of the path (pure PyTorch), ported
 # ------------------------------------------------------------------------------------------------------------
-def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit", warmup=1):
-    """Times forward + autograd backward of oracle/msda_torch_port.py on the host cores.
+def workload_string(w, loc_mode):
+    """config.workload: ONE string for both arms (the driver compares them)."""
+    return (f"{w.name}: N={w.N} per GPU, levels={[list(l) for l in w.levels]}, Lq={w.Lq}, M={w.M}, P={w.P}, D={w.D}, "
+            f"loc={loc_mode}; step = forward + backward")
 
-    Returns (Gsamples/s, ms per step, steps run, sample description, threads)."""
+
+def cpu_reference_fn():
+    """The CPU implementation of the path that is timed as the baseline: the reference's OWN
+    ``ms_deform_attn_core_pytorch`` + autograd (unmodified file bundled into the git-ignored oracle/_ref/ by
+    oracle/build_ref_py.py, kind "reference"); the port oracle/msda_torch_port.py (kind "port") only when that bundle is
+    absent.  Returns (callable, kind, description)."""
+    try:
+        from oracle import build_ref_py
+
+        if build_ref_py.bundled():
+            build_ref_py.load()
+            return build_ref_py.fwd_bwd, "reference", ("ms_deform_attn_core_pytorch + autograd, unmodified "
+                                                       "alonet/deformable_detr/ops/functions/ms_deform_attn_func.py:85-190 (oracle/_ref/alonet_ref_py)")
+    except Exception:
+        pass
+    from oracle.msda_torch_port import msda_fwd_bwd_port
+
+    return msda_fwd_bwd_port, "port", "oracle/msda_torch_port.py (port of ms_deform_attn_func.py:85-190) + autograd"
+
+
+def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit", warmup=1):
+    """Times forward + autograd backward of the reference's CPU path on the host cores.
+
+    Returns (Gsamples/s, ms per step, steps run, sample description, threads, kind)."""
     import torch
 
     from aloception_oss_b200.synthetic import Workload, torch_inputs
-    from oracle.msda_torch_port import msda_fwd_bwd_port
 
+    fn, kind, what = cpu_reference_fn()
     threads = os.cpu_count() or 1
     torch.set_num_threads(threads)
     w = workload
     x = torch_inputs(w, seed=3, loc_mode=loc_mode)
     t0 = time.perf_counter()
-    msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])  # warm-up + cost probe
+    fn(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])  # warm-up + cost probe
     probe = time.perf_counter() - t0
+    t0 = time.perf_counter()
+    fn(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])  # second probe: the first pays one-off allocations
+    probe = min(probe, time.perf_counter() - t0)
     desc = f"{w.name}: full batch N={w.N}, Lq={w.Lq}"
     if steps is not None and steps * probe > budget_s and w.Lq > 1:
         # bound the run: keep the full value pyramid, take a prefix of the queries
@@ -139,13 +167,13 @@ def cpu_port_rate(workload, budget_s, steps=None, loc_mode="unit", warmup=1):
                  grad_out=x["grad_out"][:, :lq].contiguous())
         desc = f"{workload.name}: N={w.N}, first {lq} of {workload.Lq} queries per image (bounded sample)"
     n = steps if steps is not None else max(3, min(200, int(budget_s / max(probe, 1e-4))))
-    for _ in range(max(0, warmup - 1)):  # the cost probe above was the first warm-up step
-        msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
+    for _ in range(max(0, warmup - 2)):  # the two cost probes above were the first warm-up steps
+        fn(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
     t0 = time.perf_counter()
     for _ in range(n):
-        msda_fwd_bwd_port(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
+        fn(x["value"], x["shapes"], x["loc"], x["attn"], x["grad_out"])
     dt = time.perf_counter() - t0
-    return w.samples * n / dt / 1e9, dt / n * 1e3, n, desc, threads
+    return w.samples * n / dt / 1e9, dt / n * 1e3, n, f"{desc}; {what}", threads, kind
 
 
 def run_reference(args):
@@ -156,14 +184,14 @@ def run_reference(args):
 
     w = WORKLOADS[args.workload]
     warm = max(3, min(args.warmup, 10))  # W >= 3 untimed steps (bounded: a CPU step takes ~20 ms)
-    rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=120.0, steps=args.steps, loc_mode=args.loc_mode, warmup=warm)
+    rate, ms, n, desc, threads, kind = cpu_port_rate(w, budget_s=120.0, steps=args.steps, loc_mode=args.loc_mode, warmup=warm)
     line = {
         "impl": "reference", "metric": METRIC, "value": rate, "unit": UNIT, "n_gpus": args.gpus, "steps": n,
         "warmup": warm, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": f"{w.name}: N={w.N}, levels={list(w.levels)}, Lq={w.Lq}, M={w.M}, P={w.P}, D={w.D}; "
-                               "fwd + autograd bwd of the reference's pure-PyTorch CPU path (port)"},
-        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": "port", "sample": desc},
+        "config": {"workload": workload_string(w, args.loc_mode),
+                   "implementation": "the reference's pure-PyTorch CPU path on the host cores (rank 0 only)"},
+        "cpu_baseline": {"value": rate, "unit": UNIT, "cores": threads, "kind": kind, "sample": desc},
         "e2e": {"value": rate, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -253,12 +281,18 @@ def main():
     while n_sets * step_bytes > 40e9 and n_sets > 2:
         n_sets -= 1
     sets = [device_inputs(w, seed=1000 * rank + i, device=dev, dtype=tdt, loc_mode=args.loc_mode) for i in range(n_sets)]
+    # result buffers ROTATE with the input sets (a freshly re-allocated grad_value would sit at the same address every
+    # step and stay L2-resident: 13.1 vs 14.5 us for the C2 backward, profiles/README.md)
+    for s_ in sets:
+        s_["out"] = torch.empty((w.N, w.Lq, w.M * w.D), dtype=tdt, device=dev)
+        s_["grads"] = [torch.empty_like(s_["value"]), torch.empty_like(s_["loc"]), torch.empty_like(s_["attn"])]
 
     def fwd(s):
-        return msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"])
+        return msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], out=s["out"])
 
     def bwd(s):
-        return msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"])
+        return msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"],
+                                            grads=s["grads"])
 
     def step(i):
         s = sets[i % n_sets]
@@ -284,21 +318,25 @@ def main():
                 fn(i)
         return g, _capi.kernel_launch_count() - c0
 
-    def time_graph(g, replays=1):
+    def time_graph(g, replays=1, repeats=1):
+        """`repeats` measurements of `replays` back-to-back graph replays each (events on the launching stream, barrier +
+        synchronize on both sides, max over ranks per measurement).  Returns the list of measured milliseconds."""
         g.replay()  # untimed: graph upload / first-replay cost
-        barrier()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record()
-        for _ in range(replays):
-            g.replay()
-        e1.record()
-        barrier()
-        ms = e0.elapsed_time(e1)
+        out = []
+        for _ in range(repeats):
+            barrier()
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            for _ in range(replays):
+                g.replay()
+            e1.record()
+            barrier()
+            out.append(e0.elapsed_time(e1))
         if world > 1:
-            t = torch.tensor([ms], device=dev, dtype=torch.float64)
+            t = torch.tensor(out, device=dev, dtype=torch.float64)
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
-            ms = float(t.item())
-        return ms
+            out = [float(v) for v in t.tolist()]
+        return out
 
     clocks = ClockSampler(local).start()
 
@@ -306,17 +344,21 @@ def main():
     chunk = min(K, 500)  # graph of `chunk` steps replayed K/chunk times (K rounded down to a multiple)
     reps = max(1, K // chunk)
     K_eff = chunk * reps
+    # One measurement = exactly K_eff steps.  A single short measurement is jitter-limited (K = 20 is 0.4 ms), so the
+    # measurement is repeated and the MEDIAN per-step time is reported (`steps` stays K_eff; all repeats under "timing").
+    repeats = max(5, min(50, -(-25000 // K_eff)))
     g_step, launches = capture(step, chunk)
-    ms_total = time_graph(g_step, reps)
-    ms_per_step = ms_total / K_eff
+    ms_all = time_graph(g_step, reps, repeats)
+    ms_per_step = statistics.median(ms_all) / K_eff
     value = w.samples * world / (ms_per_step * 1e-3) / 1e9
 
     # ---- per-pass timing for the roofline: forward-only and backward-only graphs -----------------------------
     g_f, lf = capture(lambda i: fwd(sets[i % n_sets]), chunk)
-    ms_fwd = time_graph(g_f, reps) / K_eff
+    ms_fwd = statistics.median(time_graph(g_f, reps, repeats)) / K_eff
     g_b, lb = capture(lambda i: bwd(sets[i % n_sets]), chunk)
-    ms_bwd = time_graph(g_b, reps) / K_eff
+    ms_bwd = statistics.median(time_graph(g_b, reps, repeats)) / K_eff
     peak, peak_src = hbm_peak()
+    touched = touched_bytes(torch, w, sets[0], elt)
 
     try:
         with open(os.path.join(ROOT, "profiles", "traffic.json")) as f:
@@ -326,12 +368,19 @@ def main():
 
     def roof(bytes_, ms, what, tkey=None):
         ach = bytes_ / (ms * 1e-3) / 1e9
+        tb = touched[tkey]
         return {"bound": "hbm", "kernel": what, "achieved": round(ach, 1), "peak": peak, "unit": "GB/s",
-                "frac": round(ach / peak, 4), "traffic": traffic.get(tkey), "algorithmic_bytes": bytes_, "us_per_launch": round(ms * 1e3, 3),
+                "frac": round(ach / peak, 4), "traffic": traffic.get(tkey), "traffic_source": "ncu --set full, profiles/traffic.json (cold-cache single launch)",
+                "algorithmic_bytes": bytes_, "us_per_launch": round(ms * 1e3, 3),
+                # SURVEY 8(d) counts the whole value tensor once although a 300-query call touches part of it: `frac` can
+                # exceed 1 on large decoder shapes.  touched_bytes counts value / grad_value rows only where a tap lands
+                # (computed from this run's sampling locations, 128-byte (row, head) granules) -- the bytes that must move.
+                "touched_bytes": tb, "frac_touched": round(tb / (ms * 1e-3) / 1e9 / peak, 4),
                 "peak_source": peak_src}
 
+    bwd_kernel = "msda_zero_kernel + msda_bwd_tile_kernel" if (w.Lq == w.S and args.dtype == "f32") else "msda_zero_kernel + msda_bwd_sg_kernel"
     r_fwd = roof(w.algorithmic_bytes(elt, False), ms_fwd, "msda_fwd_sg_kernel (forward pass)", "fwd")
-    r_bwd = roof(w.algorithmic_bytes(elt, True), ms_bwd, "msda_zero_kernel + msda_bwd_sg_kernel (backward pass, PDL-overlapped)", "bwd")
+    r_bwd = roof(w.algorithmic_bytes(elt, True), ms_bwd, bwd_kernel + " (backward pass, PDL-overlapped)", "bwd")
     dominant = r_bwd if ms_bwd >= ms_fwd else r_fwd
 
     # ---- eager (no graph) rate: what a Python caller gets launch-by-launch ------------------------------------
@@ -359,9 +408,9 @@ def main():
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
         os.sched_setaffinity(0, all_cpus)  # the CPU baseline gets every host core again
-        rate, ms, n, desc, threads = cpu_port_rate(w, budget_s=12.0, loc_mode=args.loc_mode)
-        cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": "port",
-                    "sample": f"{desc}; {n} steps of fwd+autograd-bwd, {ms:.1f} ms/step (oracle/msda_torch_port.py)"}
+        rate, ms, n, desc, threads, kind = cpu_port_rate(w, budget_s=12.0, loc_mode=args.loc_mode)
+        cpu_base = {"value": rate, "unit": UNIT, "cores": threads, "kind": kind,
+                    "sample": f"{desc}; {n} steps of fwd+autograd-bwd, {ms:.1f} ms/step"}
 
     if rank == 0:
         line = {
@@ -369,14 +418,16 @@ def main():
             "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": args.dtype, "data": "synthetic",
             "config": {
-                "workload": f"{w.name} per GPU: N={w.N}, levels={[list(l) for l in w.levels]}, Lq={w.Lq}, M={w.M}, "
-                            f"P={w.P}, D={w.D}, loc={args.loc_mode}; step = forward + backward",
+                "workload": workload_string(w, args.loc_mode),
                 "samples_per_step_per_gpu": w.samples,
-                "l2_policy": f"rotating {n_sets} distinct input sets ({n_sets * step_bytes / 1e6:.0f} MB nominal, >= 8x the 126 MB L2)",
-                "launch": f"CUDA graph of {chunk} steps x {reps} replays",
+                "l2_policy": f"rotating {n_sets} distinct sets of inputs AND result buffers (out, grad_value, grad_loc, grad_attn) "
+                             f"({n_sets * step_bytes / 1e6:.0f} MB nominal, >= 8x the 126 MB L2): no tensor of a step is L2-resident from the step before",
+                "launch": f"CUDA graph of {chunk} steps x {reps} replays = {K_eff} steps per measurement; {repeats} measurements, median reported",
                 "sharding": "batch-sharded, no data-path collective",
                 "host": numa_note,
             },
+            "timing": {"measurements": repeats, "steps_per_measurement": K_eff,
+                       "ms_per_step_min": min(ms_all) / K_eff, "ms_per_step_median": ms_per_step, "ms_per_step_max": max(ms_all) / K_eff},
             "roofline": dominant, "roofline_fwd": r_fwd, "roofline_bwd": r_bwd,
             "fwd_only": {"value": w.samples * world / (ms_fwd * 1e-3) / 1e9, "unit": UNIT, "us": ms_fwd * 1e3},
             "bwd_only": {"value": w.samples * world / (ms_bwd * 1e-3) / 1e9, "unit": UNIT, "us": ms_bwd * 1e3},
@@ -390,6 +441,36 @@ def main():
         emit(line)
     if world > 1:
         dist.destroy_process_group()
+
+
+def touched_bytes(torch, w, s, elt):
+    """Bytes a call MUST move given its sampling locations: like SURVEY 8(d)'s algorithmic bytes, but the value tensor
+    (forward, backward gather) is counted only where a bilinear tap lands -- distinct (image, pixel, head) rows of D
+    elements.  grad_value is still written in full (zero-fill).  Computed on the device from one input set."""
+    N, S, M, D, L, P, Lq = w.N, w.S, w.M, w.D, w.L, w.P, w.Lq
+    loc = s["loc"].float()
+    shapes = s["shapes"].long()
+    start = s["start"].long()
+    hit = torch.zeros((N * S * M,), dtype=torch.bool, device=loc.device)
+    n_idx = torch.arange(N, device=loc.device).view(N, 1, 1, 1)
+    m_idx = torch.arange(M, device=loc.device).view(1, 1, M, 1)
+    for l in range(L):
+        H, W = int(shapes[l, 0]), int(shapes[l, 1])
+        x = loc[:, :, :, l, :, 0] * W - 0.5
+        y = loc[:, :, :, l, :, 1] * H - 0.5
+        inside = (x > -1) & (y > -1) & (x < W) & (y < H)
+        x0, y0 = torch.floor(x).long(), torch.floor(y).long()
+        for dy in (0, 1):
+            for dx in (0, 1):
+                xx, yy = x0 + dx, y0 + dy
+                ok = inside & (xx >= 0) & (xx < W) & (yy >= 0) & (yy < H)
+                row = (n_idx * S + int(start[l]) + yy.clamp(0, H - 1) * W + xx.clamp(0, W - 1)) * M + m_idx
+                hit[row[ok]] = True
+    rows = int(hit.sum().item())
+    nsmd, nqmlp, nqmd = N * S * M * D, N * Lq * M * L * P, N * Lq * M * D
+    return {"fwd": elt * (rows * D + 3 * nqmlp + nqmd) + 12 * L,
+            "bwd": elt * (rows * D + nsmd + 6 * nqmlp + nqmd) + 12 * L,
+            "value_rows_touched": rows, "value_rows_total": N * S * M}
 
 
 def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
@@ -438,7 +519,7 @@ def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
     h2d = sum(n for _, n, _ in in_lay) * esz
     d2h = sum(n for _, n, _ in out_lay) * esz
 
-    def run(n):
+    def run(n, compute=True):
         for i in range(n):
             sl = slots[i % depth]
             with torch.cuda.stream(s_up):
@@ -449,8 +530,9 @@ def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
                 s_cp.wait_event(sl["ev_up"])
                 s_cp.wait_event(sl["ev_down"])  # slot outputs are free once their previous download finished
                 x, o = sl["in"], sl["out"]
-                msda.ms_deform_attn_forward(x["value"], shapes, start, x["loc"], x["attn"], out=o[0])
-                msda.ms_deform_attn_backward(x["value"], shapes, start, x["loc"], x["attn"], x["grad_out"], grads=o[1:])
+                if compute:
+                    msda.ms_deform_attn_forward(x["value"], shapes, start, x["loc"], x["attn"], out=o[0])
+                    msda.ms_deform_attn_backward(x["value"], shapes, start, x["loc"], x["attn"], x["grad_out"], grads=o[1:])
                 sl["ev_done"].record(s_cp)
             with torch.cuda.stream(s_dn):
                 s_dn.wait_event(sl["ev_done"])
@@ -481,8 +563,23 @@ def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
         t = torch.tensor([ms], device=dev, dtype=torch.float64)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms = float(t.item())
+    # the same pipeline with the kernels left out: what the host<->device link alone allows (all ranks copy at once)
+    if world > 1:
+        dist.barrier()
+    t0 = time.perf_counter()
+    run(K, compute=False)
+    torch.cuda.synchronize()
+    ms_copy = (time.perf_counter() - t0) * 1e3 / K
+    if world > 1:
+        t = torch.tensor([ms_copy], device=dev, dtype=torch.float64)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_copy = float(t.item())
     return {"value": w.samples * world / (ms * 1e-3) / 1e9, "unit": UNIT, "h2d_bytes_per_step": int(h2d),
             "d2h_bytes_per_step": int(d2h), "ms_per_step": ms, "steps": K,
+            "copy_only_ms_per_step": ms_copy,
+            "link_gbs_each_way_all_ranks": round(world * max(h2d, d2h) / (ms_copy * 1e-3) / 1e9, 1),
+            "limit": ("host<->device copies: the same pipeline WITHOUT the kernels takes "
+                      f"{ms_copy:.3f} ms/step ({100 * ms_copy / ms:.0f} % of the e2e step); H2D and D2H of all ranks share the host's PCIe / memory path"),
             "path": "pinned host arena -> 1 H2D -> ms_deform_attn_forward + ms_deform_attn_backward (C ABI) -> 1 D2H of out, "
                     "grad_value, grad_loc, grad_attn; 3-slot pipeline on 3 streams; host wall clock"}
 

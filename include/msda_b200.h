@@ -174,6 +174,11 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *   "zero_mode"        0=auto, 1=128-bit store kernel, 2=TMA bulk-store kernel (zero fill of grad_value)
  *   "zero_ctas"        0=default, else zero-fill CTAs per SM;  "zero_threads" threads per zero-fill CTA;
  *   "zero_chunk_kb"    bytes per TMA bulk store of the zero fill, in KB
+ *   "bwd_tile_mode"    0=auto (off), 1=unit-ordered backward, 2=tile-binned backward (msda_bwd_tile.cuh: query-tiled
+ *                      privatised accumulation of grad_value -- records counting-sorted by destination in shared memory,
+ *                      summed in registers, ONE red per destination and tile; fp32, D = 32, P = 4, L <= 16, S <= 2^19,
+ *                      16-byte aligned tensors; other problems keep the unit-ordered kernel)
+ *   "bwd_tile_ctas"    0=2, else persistent CTAs per SM of the tile-binned backward (1 or 2)
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

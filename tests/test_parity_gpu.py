@@ -24,7 +24,7 @@ def _ops(cuda_device):
     msda.load_ops()
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
               "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
-              "zero_threads", "zero_chunk_kb", "spec_mode"):
+              "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas"):
         _capi.set_tuning(k, 0)
     yield
 
