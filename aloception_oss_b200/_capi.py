@@ -20,6 +20,7 @@ HEADER = os.path.join(ROOT, "include", "msda_b200.h")
 ABI_VERSION = 1
 F32, BF16, F16, F64 = 0, 1, 2, 3
 BWD_PREZEROED = 1  # MSDA_BWD_PREZEROED
+BWD_DETERMINISTIC = 2  # MSDA_BWD_DETERMINISTIC
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -61,6 +62,36 @@ def build_library(force: bool = False, verbose: bool = False) -> str:
     return LIB_PATH
 
 
+SHIM_PATH = os.path.join(_PKG, "libmsda_torch_shim.so")
+SHIM_SRC = os.path.join(CSRC, "msda_torch_shim.cpp")
+
+
+def shim_enabled() -> bool:
+    """The C++ torch-op registration (csrc/msda_torch_shim.cpp) is used when it has been built, unless MSDA_NO_SHIM=1 or an
+    experimental library is selected with MSDA_LIB_PATH (the shim is linked against the product library)."""
+    return (os.environ.get("MSDA_NO_SHIM", "0") != "1" and not os.environ.get("MSDA_LIB_PATH") and os.path.exists(SHIM_PATH)
+            and os.path.exists(LIB_PATH))
+
+
+def build_shim(force: bool = False) -> str:
+    """Compile csrc/msda_torch_shim.cpp against the installed torch (g++, no nvcc) into the in-tree libmsda_torch_shim.so."""
+    deps = [SHIM_SRC, HEADER, LIB_PATH]
+    if not force and os.path.exists(SHIM_PATH) and all(os.path.getmtime(d) <= os.path.getmtime(SHIM_PATH) for d in deps if os.path.exists(d)):
+        return SHIM_PATH
+    import torch
+
+    tl = os.path.dirname(os.path.abspath(torch.__file__))
+    cuda_home = os.environ.get("CUDA_HOME", "/usr/local/cuda")
+    cmd = ["g++", "-O2", "-std=c++17", "-fPIC", "-shared", f"-D_GLIBCXX_USE_CXX11_ABI={int(torch._C._GLIBCXX_USE_CXX11_ABI)}",
+           f"-I{tl}/include", f"-I{tl}/include/torch/csrc/api/include", f"-I{cuda_home}/include", SHIM_SRC, "-o", SHIM_PATH,
+           f"-L{_PKG}", "-lmsda_b200", f"-L{tl}/lib", "-ltorch", "-ltorch_cpu", "-lc10", "-lc10_cuda", "-ltorch_cuda",
+           "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath,{tl}/lib"]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    if res.returncode != 0:
+        raise RuntimeError("g++ failed:\n" + " ".join(cmd) + "\n" + res.stdout + res.stderr)
+    return SHIM_PATH
+
+
 _lib = None
 
 
@@ -87,6 +118,8 @@ def lib() -> ctypes.CDLL:
     L.msda_forward_host.argtypes = [vp] * 6 + [dp, i, vp]
     L.msda_backward_workspace_bytes.restype = sz
     L.msda_backward_workspace_bytes.argtypes = [dp, i]
+    L.msda_backward_workspace_bytes_ex.restype = sz
+    L.msda_backward_workspace_bytes_ex.argtypes = [dp, i, i]
     L.msda_backward.restype = i
     L.msda_backward.argtypes = [vp] * 10 + [sz, dp, i, i, vp]
     L.msda_zero_fill.restype = i

@@ -185,7 +185,11 @@ int pick_unroll(int knob, int fallback) {
 template <typename T, int D, int MC, bool FUSED = false>
 int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
                    void* out, const msda_dims& d, cudaStream_t st, const void* ref = nullptr, int ref_dim = 0) {
-  const int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
+  int U = pick_unroll(g_fwd_unroll.load(std::memory_order_relaxed), 1);
+  // the rounds of a pass address samples k0 + j*G + g < 32 (one per lane): G * U must not exceed the warp.  16-bit rows of
+  // D = 16 channels are covered by 2 lanes (G = 16 lane groups), so the "fwd_unroll = 4" knob is clamped to 2 there
+  constexpr int G = 32 / (D / msda::Vec16<T>::N);
+  while (G * U > 32) U >>= 1;
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
   const bool pdl = false;  // forward kernels launch normally (see pdl_wait / pdl_trigger in msda_kernels.cuh)
@@ -358,10 +362,10 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   return check_pdl_launch(e, "msda_backward(zero grad_value)");
 }
 
-template <typename T, int D, int MC, bool FUSED = false>
+template <typename T, int D, int MC, bool FUSED = false, bool DET = false>
 int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
                    const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st,
-                   const void* ref = nullptr, int ref_dim = 0, float* gref = nullptr) {
+                   const void* ref = nullptr, int ref_dim = 0, float* gref = nullptr, const unsigned* det_hdr = nullptr) {
   const int U = pick_unroll(g_bwd_unroll.load(std::memory_order_relaxed), 1);
   const Launch l = image_launch(d, 2);
   const float inv_p = 1.0f / (float)(d.num_point > 0 ? d.num_point : 1);
@@ -377,7 +381,7 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   // Only when the fill is short (grad_value fits in L2): behind a long fill the early-launched CTAs would just sit on
   // the SMs the fill needs (C4DEC, 728 MB: 298 us with PDL vs 290 us without).
   const size_t fill_bytes = sizeof(float) * (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
-  const bool pdl = !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20) && !t_prezeroed;
+  const bool pdl = !DET && !g_no_pdl.load(std::memory_order_relaxed) && fill_bytes <= (96u << 20) && !t_prezeroed;
   attr[0].val.programmaticStreamSerializationAllowed = pdl ? 1 : 0;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
@@ -387,9 +391,10 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   const int hm = l.head_major;
   cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
-  e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED>, go_, value_, shapes, start, loc_, attn_, \
-                         gv, gloc_, gattn_, S, M, L, P, inv_p, QM, ref_, ref_dim, gref, hm)
-  if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4);
+  e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED, DET>, go_, value_, shapes, start, loc_, attn_, \
+                         gv, gloc_, gattn_, S, M, L, P, inv_p, QM, ref_, ref_dim, gref, hm, det_hdr)
+  if constexpr (DET) { MSDA_BWD(1); }
+  else { if (U == 1) MSDA_BWD(1); else if (U == 2) MSDA_BWD(2); else MSDA_BWD(4); }
 #undef MSDA_BWD
   g_launches.fetch_add(1, std::memory_order_relaxed);
   if (e != cudaSuccess) {
@@ -454,6 +459,61 @@ int launch_bwd_tile(const void* go, const void* value, const int32_t* shapes, co
                                            (const float*)attn, gv, (float*)gloc, (float*)gattn, d.batch, d.spatial_size,
                                            d.num_heads, d.num_levels, d.num_query);
   return check_pdl_launch(e, "msda_backward(tile)");
+}
+
+// Deterministic backward (MSDA_BWD_DETERMINISTIC): int64 fixed-point accumulation of grad_value (msda_kernels.cuh).
+// workspace = [256-byte header: max|grad_out|, max|attn| bit patterns][int64 image of grad_value].
+constexpr size_t kDetHeader = 256;
+
+template <typename T>
+int backward_deterministic(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                           const void* attn, void* grad_value, void* gloc, void* gattn, void* workspace, const msda_dims& d,
+                           long long units, cudaStream_t st) {
+  const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
+  unsigned* hdr = (unsigned*)workspace;
+  long long* img = (long long*)((char*)workspace + kDetHeader);
+  if (n_value == 0) return 0;
+  cudaError_t ce = cudaMemsetAsync(hdr, 0, kDetHeader, st);
+  if (ce != cudaSuccess) return fail("msda_backward(deterministic): cudaMemsetAsync: %s", cudaGetErrorString(ce));
+  const bool has_samples = units > 0 && d.num_levels * d.num_point > 0;
+  if (has_samples) {
+    const long long n_go = units * d.channels, n_attn = units * d.num_levels * d.num_point;
+    long long blocks = (n_go + 256 * 8 - 1) / (256 * 8);
+    if (blocks > 148 * 8) blocks = 148 * 8;
+    msda::msda_absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)go, n_go, (const T*)attn, n_attn, hdr);
+    if (int rc = check_launch("msda_backward(deterministic: absmax)")) return rc;
+  }
+  if (int rc = zero_fill(img, n_value * sizeof(long long), st)) return rc;
+  if (has_samples) {
+    int rc = -1;
+#define MSDA_CASE(DD)                                                                                                   \
+  case DD:                                                                                                              \
+    rc = d.num_heads == 8 ? launch_bwd_vec<T, DD, 8, false, true>(go, value, shapes, start, loc, attn, (float*)img, gloc,  \
+                                                                  gattn, d, st, nullptr, 0, nullptr, hdr)                \
+                          : launch_bwd_vec<T, DD, 0, false, true>(go, value, shapes, start, loc, attn, (float*)img, gloc,  \
+                                                                  gattn, d, st, nullptr, 0, nullptr, hdr);               \
+    break;
+    switch (d.channels) {
+#ifndef MSDA_DEV_FAST
+      MSDA_CASE(16)
+      MSDA_CASE(64)
+      MSDA_CASE(128)
+#endif
+      MSDA_CASE(32)
+      default: break;
+    }
+#undef MSDA_CASE
+    if (rc != 0) return rc > 0 ? rc : fail("msda_backward(deterministic): unsupported channel count %d", d.channels);
+  }
+  long long blocks = (long long)((n_value + 256 * 8 - 1) / (256 * 8));
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  msda::msda_det_cvt_kernel<T><<<(unsigned)blocks, 256, 0, st>>>(img, (T*)grad_value, (long long)n_value, hdr);
+  return check_launch("msda_backward(deterministic: convert grad_value)");
+}
+
+bool det_shape_ok(const msda_dims& d, int dtype) {
+  return vec_shape_ok(d) && dtype != MSDA_F64 && (d.channels == 16 || d.channels == 32 || d.channels == 64 || d.channels == 128) &&
+         (long long)d.num_query * d.num_levels * d.num_point <= (1LL << 25);
 }
 
 template <typename T>
@@ -673,12 +733,15 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
   return fail("unreachable");
 }
 
-size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype) {
+size_t msda_backward_workspace_bytes_ex(const msda_dims* dims, int dtype, int flags) {
   if (!dims) return 0;
-  if (dtype == MSDA_BF16 || dtype == MSDA_F16)
-    return sizeof(float) * (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+  const size_t n_value = (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
+  if (flags & MSDA_BWD_DETERMINISTIC) return n_value ? kDetHeader + sizeof(long long) * n_value : 0;
+  if (dtype == MSDA_BF16 || dtype == MSDA_F16) return sizeof(float) * n_value;
   return 0;
 }
+
+size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype) { return msda_backward_workspace_bytes_ex(dims, dtype, 0); }
 
 int msda_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
                   const int32_t* level_start_index, const void* sampling_loc, const void* attn_weight,
@@ -686,7 +749,9 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
                   size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream) {
   g_err[0] = 0;
   if (int rc = validate_dims(dims, dtype)) return rc;
-  if (flags & ~MSDA_BWD_PREZEROED) return fail("unknown flags 0x%x", flags);
+  if (flags & ~(MSDA_BWD_PREZEROED | MSDA_BWD_DETERMINISTIC)) return fail("unknown flags 0x%x", flags);
+  const bool det = (flags & MSDA_BWD_DETERMINISTIC) != 0;
+  if (det && (flags & MSDA_BWD_PREZEROED)) return fail("MSDA_BWD_DETERMINISTIC cannot be combined with MSDA_BWD_PREZEROED");
   struct Prezeroed {  // scoped: every return path clears it
     explicit Prezeroed(bool v) { t_prezeroed = v; }
     ~Prezeroed() { t_prezeroed = false; }
@@ -694,7 +759,7 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
   const msda_dims& d = *dims;
   const long long units = (long long)d.batch * d.num_query * d.num_heads;
   const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
-  const size_t need = msda_backward_workspace_bytes(dims, dtype);
+  const size_t need = msda_backward_workspace_bytes_ex(dims, dtype, flags);
   if (need > 0 && n_value > 0 && (!workspace || workspace_bytes < need))
     return fail("workspace too small: need %zu bytes, got %zu", need, workspace_bytes);
   if (n_value > 0 && !grad_value) return fail("grad_value is NULL");
@@ -704,6 +769,21 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
     return fail("NULL tensor pointer passed to msda_backward");
   if ((units + 7) / 8 > 0x7fffffffLL) return fail("problem too large for one launch");
   cudaStream_t st = (cudaStream_t)stream;
+  if (det) {
+    const bool al = aligned(value, 16) && aligned(grad_output, 16) && aligned(workspace, 16) && aligned(sampling_loc, 8) &&
+                    aligned(grad_sampling_loc, 8);
+    if (!det_shape_ok(d, dtype) || (has_samples && !al))
+      return fail("MSDA_BWD_DETERMINISTIC is served by the vector kernels only (f32 / bf16 / f16, D in {16, 32, 64, 128}, "
+                  "16-byte aligned tensors, Lq * L * P <= 2^25)");
+    switch (dtype) {
+      case MSDA_F32: return backward_deterministic<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+#ifndef MSDA_DEV_FAST
+      case MSDA_BF16: return backward_deterministic<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+      case MSDA_F16: return backward_deterministic<__half>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+#endif
+      default: return fail("MSDA_BWD_DETERMINISTIC: unsupported dtype %d", dtype);
+    }
+  }
   switch (dtype) {
     case MSDA_F32: return backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
 #ifndef MSDA_DEV_FAST

@@ -1118,6 +1118,48 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
 }
 
 // ------------------------------------------------------------------------------------------------
+// DETERMINISTIC accumulation of grad_value (C-ABI flag MSDA_BWD_DETERMINISTIC)
+// ------------------------------------------------------------------------------------------------
+// fp32 atomics make grad_value depend on the order in which the reds reach L2 (the reference's atomicAdd scatter has the same
+// property: ms_deform_im2col_cuda.cuh:125-152).  In deterministic mode every contribution  c = weight * grad_out  (one fp32
+// product, as in the default path) is converted to FIXED POINT,  q = rint(c * 2^k),  and accumulated with 64-bit INTEGER reds:
+// integer addition is associative, so the sum is the same bit pattern whatever the order.  2^k is derived from max|grad_out|
+// and max|attn| of the call (header of the workspace, written by msda_absmax_kernel) so that |q| <= 2^37 and 2^25 contributions
+// per element cannot overflow; the absolute error per contribution is 2^-37 of the largest possible contribution -- finer than
+// the fp32 accumulation it replaces.  msda_det_cvt_kernel turns the sums into grad_value (one rounding per element).
+__device__ __forceinline__ int det_shift(const unsigned* __restrict__ hdr) {
+  const int eg = (int)((__ldg(hdr) >> 23) & 255u) - 127;      // floor(log2(max |grad_out|)); -127 for zero / denormals
+  const int ea = (int)((__ldg(hdr + 1) >> 23) & 255u) - 127;  // floor(log2(max |attn|))
+  const int k = 36 - (eg + 1) - max(ea + 1, 0);
+  return max(-250, min(250, k));  // applied as two exact power-of-two factors 2^(k/2) * 2^(k - k/2)
+}
+__device__ __forceinline__ float pow2_int(int k) { return __int_as_float((k + 127) << 23); }  // exact 2^k, -126 <= k <= 127
+
+template <typename T>
+__global__ void __launch_bounds__(256) msda_absmax_kernel(const T* __restrict__ a, long long na, const T* __restrict__ b, long long nb,
+                                                          unsigned* __restrict__ hdr) {
+  float ma = 0.f, mb = 0.f;
+  const long long stride = (long long)gridDim.x * blockDim.x, i0 = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+  for (long long i = i0; i < na; i += stride) ma = fmaxf(ma, fabsf((float)to_acc(a[i])));
+  for (long long i = i0; i < nb; i += stride) mb = fmaxf(mb, fabsf((float)to_acc(b[i])));
+  ma = warp_max(ma);
+  mb = warp_max(mb);
+  if ((threadIdx.x & 31) == 0) {  // non-negative floats order like their bit patterns
+    atomicMax(hdr, __float_as_uint(ma));
+    atomicMax(hdr + 1, __float_as_uint(mb));
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(256) msda_det_cvt_kernel(const long long* __restrict__ src, T* __restrict__ dst, long long n,
+                                                           const unsigned* __restrict__ hdr) {
+  const int k = det_shift(hdr);
+  const long long stride = (long long)gridDim.x * blockDim.x;
+  for (long long i = (long long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride)
+    dst[i] = from_acc<T>((float)scalbn((double)src[i], -k));
+}
+
+// ------------------------------------------------------------------------------------------------
 // VECTOR BACKWARD
 // ------------------------------------------------------------------------------------------------
 // grad_value accumulates in fp32 (`gv`): the caller's tensor for T=float, a workspace for 16-bit T.
@@ -1135,14 +1177,15 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
 // FUSED: `loc` / `attn` are the raw offsets / logits, `gloc` / `gattn` receive the gradients w.r.t. THOSE (softmax and
 // location arithmetic differentiated in the kernel), `gref` (fp32, pre-zeroed, may be null) accumulates the gradient
 // w.r.t. the reference points with scalar reds (M*P contributions per element).
-template <typename T, int D, int MC, int U, bool FUSED>
-__global__ void __maxnreg__(U == 1 ? (FUSED ? MSDA_BWD_MAX_REGS_FUSED : MSDA_BWD_MAX_REGS) : (U == 2 ? 80 : 128))
+// DET: `gv` is the int64 fixed-point image (see above), `det_hdr` its header; launched WITHOUT programmatic dependency.
+template <typename T, int D, int MC, int U, bool FUSED, bool DET = false>
+__global__ void __maxnreg__(U == 1 ? (FUSED ? MSDA_BWD_MAX_REGS_FUSED : (DET ? 64 : MSDA_BWD_MAX_REGS)) : (U == 2 ? 80 : 128))
 msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
                    T* __restrict__ gloc, T* __restrict__ gattn,
                    int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
-                   float* __restrict__ gref, int head_major) {
+                   float* __restrict__ gref, int head_major, const unsigned* __restrict__ det_hdr = nullptr) {
   using IO = VecIO<T, BwdGranule<T>::VB>;
   constexpr int VEC = IO::N;
   constexpr int LPR = D / VEC;
@@ -1162,6 +1205,12 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   const long long voff = (long long)blockIdx.y * S * MD + (m * D + cl * VEC);
   const T* __restrict__ vb = value + voff;
   float* __restrict__ gb = gv + voff;
+  float det_s1 = 0.f, det_s2 = 0.f;
+  if constexpr (DET) {
+    const int k = det_shift(det_hdr);
+    det_s1 = pow2_int(k / 2);
+    det_s2 = pow2_int(k - k / 2);
+  }
 
   float go[VEC];
   IO::unpack(IO::load(grad_out + u * D + cl * VEC), go);
@@ -1252,6 +1301,18 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         w[1] = __shfl_sync(0xffffffffu, w01, src);
         w[2] = __shfl_sync(0xffffffffu, w10, src);
         w[3] = __shfl_sync(0xffffffffu, w11, src);
+        if constexpr (DET) {
+          unsigned long long* g0 = reinterpret_cast<unsigned long long*>(gv) + (voff + off[j]);
+          unsigned long long* g1 = g0 + (rsf[j] >> 4);
+          unsigned long long* gp[4] = {g0, g0 + MD, g1, g1 + MD};
+#pragma unroll
+          for (int t = 0; t < 4; ++t)
+            if (rsf[j] & (1 << t)) {
+#pragma unroll
+              for (int i = 0; i < VEC; ++i)  // same fp32 product as the default path, then exact scaling by 2^k and one rint
+                atomicAdd(gp[t] + i, (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(__fmul_rn(w[t], go[i]), det_s1), det_s2)));
+            }
+        } else {
         float* g0 = gb + off[j];
         float* g1 = g0 + (rsf[j] >> 4);
         float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
@@ -1265,6 +1326,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
               red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
             }
           }
+        }
       }
     }
     const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0

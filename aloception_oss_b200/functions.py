@@ -25,12 +25,21 @@ from torch.autograd import Function
 from torch.autograd.function import once_differentiable
 
 from . import _capi
+from . import torch_ops as _torch_ops
 
 # MSDA_EARLY_ZERO_FILL=1: MSDeformAttnFunction starts the backward's zero-fill on a side stream during the forward pass.
 # Off by default: with the backward directly behind the forward it is SLOWER than the in-stream zero-fill -> scatter pair
 # under programmatic dependent launch (C2 step 19.3 -> 21.4 us, profiles/r1_sweep_rejected_early_zero_fill.jsonl: the
 # cross-stream fork / join costs more than the 4.9 us fill it hides); it can only pay when other work separates the two.
 EARLY_ZERO_FILL = os.environ.get("MSDA_EARLY_ZERO_FILL", "0") == "1"
+# MSDA_DETERMINISTIC=1 (or torch.use_deterministic_algorithms(True)): the backward accumulates grad_value in 64-bit fixed
+# point (C-ABI flag MSDA_BWD_DETERMINISTIC) -- bit-reproducible, unlike the reference's atomicAdd scatter
+# (ms_deform_im2col_cuda.cuh:125-152) and the default red-based path here.
+DETERMINISTIC = os.environ.get("MSDA_DETERMINISTIC", "0") == "1"
+
+
+def deterministic_requested() -> bool:
+    return DETERMINISTIC or torch.are_deterministic_algorithms_enabled()
 
 _DTYPES = {torch.float32: _capi.F32, torch.bfloat16: _capi.BF16, torch.float16: _capi.F16, torch.float64: _capi.F64}
 
@@ -139,6 +148,11 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     """CUDA forward: (N,S,M,D), (L,2) i32, (L,) i32, (N,Lq,M,L,P,2), (N,Lq,M,L,P) -> (N, Lq, M*D).
 
     ``out`` (optional) is a caller-provided result buffer, e.g. a view into a packed staging arena."""
+    if (out is None and _torch_ops.using_shim() and value.is_cuda and sampling_loc.is_cuda and attn_weight.is_cuda
+            and spatial_shapes.is_cuda and level_start_index.is_cuda):
+        # C++ entry: same checks and messages, no ctypes (csrc/msda_torch_shim.cpp)
+        return torch.ops.alonet_custom.ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                              im2col_step)
     dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step)
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
@@ -197,12 +211,22 @@ def begin_backward_zero_fill(value):
 
 
 def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_output,
-                            im2col_step=64, grads=None, prezeroed=None):
+                            im2col_step=64, grads=None, prezeroed=None, deterministic=None):
     """CUDA backward -> [grad_value, grad_sampling_loc, grad_attn_weight] (ms_deform_attn_cuda.cu:83-153).
+
+    ``deterministic`` (None = follow MSDA_DETERMINISTIC / torch.use_deterministic_algorithms): bit-reproducible grad_value
+    through 64-bit fixed-point accumulation (include/msda_b200.h, MSDA_BWD_DETERMINISTIC); float32 / bfloat16 / float16 with
+    D in {16, 32, 64, 128}; float64 and other channel counts raise.
 
     ``grads`` (optional): three caller-provided result buffers shaped like value / sampling_loc / attn_weight.
     ``prezeroed`` (optional): handle from ``begin_backward_zero_fill(value)``; its buffer becomes grad_value (fp32 / fp64) or
     the accumulation workspace (16-bit types) and the library's own zero-fill is skipped."""
+    if (grads is None and prezeroed is None and deterministic is None and _torch_ops.using_shim() and value.is_cuda
+            and sampling_loc.is_cuda and attn_weight.is_cuda and spatial_shapes.is_cuda and level_start_index.is_cuda
+            and grad_output.is_cuda):
+        # C++ entry (csrc/msda_torch_shim.cpp): same checks, same C call, no ctypes; it honours an implicit deterministic request
+        return torch.ops.alonet_custom.ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_loc, attn_weight,
+                                                               grad_output, im2col_step)
     dims = _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step,
                           extra=(("grad_output", grad_output),))
     if grad_output.numel() != dims.batch * dims.num_query * dims.num_heads * dims.channels:
@@ -211,15 +235,23 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     start = _meta_i32(level_start_index, "level_start_index")
     L = _capi.lib()
     dt = _DTYPES[value.dtype]
-    ws_bytes = L.msda_backward_workspace_bytes(ctypes.byref(dims), dt)
-    flags, pre_gv, ws = 0, None, None
+    det = deterministic_requested() if deterministic is None else bool(deterministic)
+    if det and deterministic is None and (value.dtype == torch.float64 or dims.channels not in (16, 32, 64, 128)):
+        det = False  # (an implicit request must not break float64 gradcheck / odd channel counts: they keep the reds)
+    flags, pre_gv, ws = (_capi.BWD_DETERMINISTIC if det else 0), None, None
+    if det and prezeroed is not None:
+        if deterministic is None:
+            det, flags = False, 0  # an implicit request gives way to the caller's explicit early zero-fill
+        else:
+            raise RuntimeError("deterministic=True cannot be combined with prezeroed=")
+    ws_bytes = L.msda_backward_workspace_bytes_ex(ctypes.byref(dims), dt, flags)
     if prezeroed is not None:
         if prezeroed.shape != tuple(value.shape) or prezeroed.dtype != value.dtype or prezeroed.buffer.device != value.device:
             raise RuntimeError("prezeroed handle was made for a different value tensor")
         cur = torch.cuda.current_stream(value.device)
         cur.wait_event(prezeroed.event)
         prezeroed.buffer.record_stream(cur)  # allocated on the side stream, used (and possibly freed) on this one
-        flags = _capi.BWD_PREZEROED
+        flags |= _capi.BWD_PREZEROED
         if ws_bytes:
             ws = prezeroed.buffer
         else:
@@ -371,7 +403,7 @@ class MSDeformAttnFunction(Function):
         # the backward's zero-fill starts now, on a side stream, when a backward can follow (knob: EARLY_ZERO_FILL); not
         # under CUDA-graph capture, where the side stream could stay unjoined if the backward is not captured
         ctx.prezeroed = None
-        if (EARLY_ZERO_FILL and value.is_cuda and any(ctx.needs_input_grad) and value.numel()
+        if (EARLY_ZERO_FILL and not deterministic_requested() and value.is_cuda and any(ctx.needs_input_grad) and value.numel()
                 and not torch.cuda.is_current_stream_capturing()):
             ctx.prezeroed = begin_backward_zero_fill(value)
         output = torch.ops.alonet_custom.ms_deform_attn_forward(
@@ -397,13 +429,51 @@ class MSDeformAttnFunction(Function):
         return grad_value, None, None, grad_sampling_loc, grad_attn_weight, None
 
 
-def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights):
+def _bilinear_sample_gather(img, grid):
+    """Bilinear sampling with zero padding, ``align_corners=False``, from gather + arithmetic only.
+
+    img (B, C, H, W); grid (B, Hg, Wg, 2) in [-1, 1], (x, y) order -> (B, C, Hg, Wg).  Same function as
+    ``F.grid_sample(img, grid, "bilinear", "zeros", False)``; the reference spells it out by hand for the same reason
+    (ms_deform_attn_func.py:99-102, 110-190): a ``GridSample`` node needs ONNX opset >= 16 and is not understood by its
+    TensorRT tool chain, and padding an N-d tensor is replaced by concatenation ("TRT < 8.5.1", :153-160)."""
+    B, C, H, W = img.shape
+    _, Hg, Wg, _ = grid.shape
+    x = ((grid[..., 0] + 1) * W - 1) / 2  # pixel coordinates, pixel centres at integers
+    y = ((grid[..., 1] + 1) * H - 1) / 2
+    x = x.reshape(B, -1)
+    y = y.reshape(B, -1)
+    x_lo = torch.floor(x)
+    y_lo = torch.floor(y)
+    fx = x - x_lo
+    fy = y - y_lo
+    # one ring of zeros around the image (concatenations, not F.pad): index 0 and H+1 / W+1 are the zero border
+    zc = img.new_zeros((B, C, H, 1))
+    ring = torch.cat((zc, img, zc), dim=3)
+    zr = img.new_zeros((B, C, 1, W + 2))
+    ring = torch.cat((zr, ring, zr), dim=2).reshape(B, C, (H + 2) * (W + 2))
+    xi0 = (x_lo.long() + 1).clamp(0, W + 1)
+    xi1 = (x_lo.long() + 2).clamp(0, W + 1)
+    yi0 = (y_lo.long() + 1).clamp(0, H + 1)
+    yi1 = (y_lo.long() + 2).clamp(0, H + 1)
+
+    def tap(yi, xi):
+        return torch.gather(ring, 2, (yi * (W + 2) + xi).unsqueeze(1).expand(-1, C, -1))
+
+    w00 = ((1 - fx) * (1 - fy)).unsqueeze(1)
+    w01 = (fx * (1 - fy)).unsqueeze(1)
+    w10 = ((1 - fx) * fy).unsqueeze(1)
+    w11 = (fx * fy).unsqueeze(1)
+    out = tap(yi0, xi0) * w00 + tap(yi0, xi1) * w01 + tap(yi1, xi0) * w10 + tap(yi1, xi1) * w11
+    return out.reshape(B, C, Hg, Wg)
+
+
+def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations, attention_weights, use_grid_sample=False):
     """Pure-PyTorch formulation for tracing / ONNX / TensorRT export ONLY (the ``is_tracing`` branch of
     ``MSDeformAttn.forward``, reference ops/modules/ms_deform_attn.py:138-144).  It is not a fallback of the CUDA
     operator: nothing in this package routes to it unless the caller asks for the traceable graph.
 
-    Built on ``F.grid_sample(bilinear, zeros, align_corners=False)``, which is the same function as the
-    reference's hand-written ``bilinear_grid_sample`` (equal to 2e-9)."""
+    Like the reference (ms_deform_attn_func.py:85-107) the exported graph consists of split / gather / arithmetic nodes --
+    no ``GridSample``; ``use_grid_sample=True`` swaps in ``F.grid_sample`` (the same function, for exporters that have it)."""
     N, S, M, D = value.shape
     _, Lq, _, L, P, _ = sampling_locations.shape
     sizes = [(int(h), int(w)) for h, w in value_spatial_shapes]
@@ -413,7 +483,10 @@ def ms_deform_attn_core_pytorch(value, value_spatial_shapes, sampling_locations,
     for lvl, (h, w) in enumerate(sizes):
         img = levels[lvl].flatten(2).transpose(1, 2).reshape(N * M, D, h, w)
         grid = grids[:, :, :, lvl].transpose(1, 2).flatten(0, 1)
-        per_level.append(F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False))
+        if use_grid_sample:
+            per_level.append(F.grid_sample(img, grid, mode="bilinear", padding_mode="zeros", align_corners=False))
+        else:
+            per_level.append(_bilinear_sample_gather(img, grid))
     weights = attention_weights.transpose(1, 2).reshape(N * M, 1, Lq, L * P)
     out = (torch.stack(per_level, dim=-2).flatten(-2) * weights).sum(-1).view(N, M * D, Lq)
     return out.transpose(1, 2).contiguous()

@@ -9,6 +9,7 @@ from __future__ import annotations
 
 import math
 import warnings
+import weakref
 
 import torch
 import torch.nn.functional as F
@@ -17,6 +18,22 @@ from torch.nn.init import constant_, xavier_uniform_
 
 from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported,
                         load_MultiScaleDeformableAttention, ms_deform_attn_core_pytorch)
+
+
+def _graph_is_being_recorded() -> bool:
+    """True while torch.jit.trace / torch.onnx.export / torch.compile records the module: the sampling must then appear in
+    the graph as the ``alonet_custom::ms_deform_attn_forward`` node the reference's exporter looks for
+    (alonet/torch2trt/trt_exporter.py:41), not as an opaque ctypes call."""
+    if torch.jit.is_tracing() or torch.onnx.is_in_onnx_export():
+        return True
+    comp = getattr(torch, "compiler", None)
+    return bool(comp is not None and hasattr(comp, "is_compiling") and comp.is_compiling())
+
+
+# shapes tensors whose ``sum(H*W) == Len_in`` check has passed: id(tensor) -> (weak reference, version counter, Len_in).
+# Keyed on the LIVE tensor object (not on its address: the caching allocator hands a freed block to the next, different,
+# shapes tensor) and shared by all modules, so a forward pass of 12 layers on one shapes tensor validates -- and syncs -- once.
+_VALIDATED_LEVELS = {}
 
 
 def _is_power_of_2(n):
@@ -32,7 +49,6 @@ class MSDeformAttn(nn.Module):
         the locations).  ``fused=False`` reproduces the reference's op sequence."""
         super().__init__()
         self.fused = fused
-        self._validated_levels = set()
         if d_model % n_heads != 0:
             raise ValueError("d_model must be divisible by n_heads, but got {} and {}".format(d_model, n_heads))
         if not _is_power_of_2(d_model // n_heads):
@@ -53,17 +69,23 @@ class MSDeformAttn(nn.Module):
 
     def _check_level_sizes(self, input_spatial_shapes, Len_in):
         """The reference asserts ``sum_l H_l*W_l == Len_in`` on every call (ms_deform_attn.py:113), which costs a
-        device->host sync per layer when the shapes live on the GPU.  Same check here, but remembered per shapes tensor
-        (storage pointer + version counter) and skipped while a CUDA graph is being captured (a sync is illegal there)."""
-        key = (input_spatial_shapes.data_ptr(), input_spatial_shapes._version, int(Len_in))
-        if key in self._validated_levels:
+        device->host sync per layer when the shapes live on the GPU.  Same check here, but remembered per LIVE shapes tensor
+        (object identity + version counter; a new tensor is always checked, wherever the allocator put it) and skipped
+        while a CUDA graph is being captured (a sync is illegal there)."""
+        key = id(input_spatial_shapes)
+        hit = _VALIDATED_LEVELS.get(key)
+        if hit is not None and hit[0]() is input_spatial_shapes and hit[1] == input_spatial_shapes._version and hit[2] == int(Len_in):
             return
         if input_spatial_shapes.is_cuda and torch.cuda.is_current_stream_capturing():
             return
         assert (input_spatial_shapes[:, 0] * input_spatial_shapes[:, 1]).sum() == Len_in
-        if len(self._validated_levels) > 64:
-            self._validated_levels.clear()
-        self._validated_levels.add(key)
+        if len(_VALIDATED_LEVELS) > 256:
+            _VALIDATED_LEVELS.clear()
+        try:
+            ref = weakref.ref(input_spatial_shapes, lambda _r, k=key: _VALIDATED_LEVELS.pop(k, None))
+        except TypeError:
+            return
+        _VALIDATED_LEVELS[key] = (ref, input_spatial_shapes._version, int(Len_in))
 
     def _reset_parameters(self):
         # compass-pattern offset bias, zero attention logits, xavier projections (ms_deform_attn.py:70-88)
@@ -105,8 +127,9 @@ class MSDeformAttn(nn.Module):
             # operator takes ONE storage dtype -- value's -- and does its arithmetic in fp32 regardless
             reference_points = reference_points.to(value.dtype)
             offsets, weights = offsets.to(value.dtype), weights.to(value.dtype)
-        if self.fused and "is_tracing" not in kwargs and fused_supported(value, input_spatial_shapes, reference_points,
-                                                                        offsets, weights):
+        # (while a graph is being recorded the unfused op sequence runs: it goes through torch.ops.alonet_custom.*)
+        if (self.fused and "is_tracing" not in kwargs and not _graph_is_being_recorded()
+                and fused_supported(value, input_spatial_shapes, reference_points, offsets, weights)):
             output = MSDeformAttnFusedFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
                                                      reference_points.contiguous(), offsets.contiguous(),
                                                      weights.contiguous())

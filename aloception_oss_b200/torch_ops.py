@@ -14,6 +14,11 @@ import torch
 
 _lock = threading.Lock()
 _lib = None
+_shim = False  # the ops are registered by libmsda_torch_shim.so (C++: csrc/msda_torch_shim.cpp) instead of from Python
+
+
+def using_shim() -> bool:
+    return _shim
 
 FWD_SCHEMA = ("ms_deform_attn_forward(Tensor value, Tensor spatial_shapes, Tensor level_start_index, "
               "Tensor sampling_loc, Tensor attn_weight, int im2col_step) -> Tensor")
@@ -57,10 +62,21 @@ def registered() -> bool:
 
 def register() -> None:
     """Idempotent.  Raises if another library (e.g. the reference's own .so) already owns the namespace."""
-    global _lib
+    global _lib, _shim
     with _lock:
         if _lib is not None:
             return
+        from . import _capi
+
+        if _capi.shim_enabled() and not registered():
+            # C++ registration: same schemas / checks / messages, no interpreter or ctypes on the call path
+            try:
+                torch.ops.load_library(_capi.SHIM_PATH)
+                _lib, _shim = "shim", True
+                return
+            except Exception:  # stale build against another torch: fall through to the Python registration
+                if registered():
+                    raise
         try:
             lib = torch.library.Library("alonet_custom", "DEF")
         except RuntimeError as e:  # pragma: no cover - needs the reference .so in-process

@@ -74,6 +74,8 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
  * accumulation image of grad_value for the 16-bit types).
  */
 size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
+/* Same, for a call with `flags` (MSDA_BWD_DETERMINISTIC needs a 64-bit fixed-point image of grad_value + a 256-byte header). */
+size_t msda_backward_workspace_bytes_ex(const msda_dims* dims, int dtype, int flags);
 
 /*
  * Backward.  Replaces `ms_deform_attn_cuda_backward` (ms_deform_attn_cuda.cu:83-153), the dispatcher
@@ -85,8 +87,17 @@ size_t msda_backward_workspace_bytes(const msda_dims* dims, int dtype);
  * `flags`     : 0, or MSDA_BWD_PREZEROED: the caller has already zero-filled the accumulation buffer (grad_value for
  *               MSDA_F32 / MSDA_F64, `workspace` for the 16-bit types) in stream order before this call -- e.g. with
  *               msda_zero_fill() on a side stream while the forward pass ran; the library then skips its own fill.
+ *               MSDA_BWD_DETERMINISTIC: bit-reproducible grad_value.  The reference scatters with fp32 atomicAdd
+ *               (ms_deform_im2col_cuda.cuh:125-152) and so does the default path here (vectorised reds): the result depends
+ *               on the order in which the additions reach L2.  With this flag every contribution is converted to 64-bit
+ *               fixed point (scale derived from max|grad_output| and max|attn_weight| of the call) and accumulated with
+ *               integer reds -- associative, hence order-independent -- then converted back once per element.  Needs
+ *               msda_backward_workspace_bytes_ex(dims, dtype, flags) bytes of workspace; f32 / bf16 / f16, D in
+ *               {16, 32, 64, 128}, finite inputs; slower than the default (8-byte scalar reds).  grad_sampling_loc and
+ *               grad_attn_weight never depend on atomics and are bit-reproducible in either mode.
  */
 #define MSDA_BWD_PREZEROED 1
+#define MSDA_BWD_DETERMINISTIC 2
 int msda_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
                   const int32_t* level_start_index, const void* sampling_loc, const void* attn_weight,
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,

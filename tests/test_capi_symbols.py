@@ -92,18 +92,25 @@ def test_register_budgets_of_the_default_kernels():
         m = re.search(r"REG:(\d+)", line)
         if m and name:
             regs[name] = int(m.group(1))
-    bwd = [v for k, v in regs.items() if "msda_bwd_sg_kernelIfLi32ELi8ELi1ELb0" in k]
+    bwd = [v for k, v in regs.items() if "msda_bwd_sg_kernelIfLi32ELi8ELi1ELb0ELb0E" in k]  # FUSED = 0, DET = 0
     fwd = [v for k, v in regs.items() if "msda_fwd_sg_kernelIfLi32ELi8ELi1ELb0ELb1" in k]
     assert bwd and max(bwd) <= 56, bwd
     assert fwd and max(fwd) <= 40, fwd
 
 
 def test_prezeroed_flag_and_zero_fill_validation():
-    """MSDA_BWD_PREZEROED is the only defined flag bit; msda_zero_fill validates before touching the device."""
+    """MSDA_BWD_PREZEROED (1) and MSDA_BWD_DETERMINISTIC (2) are the defined flag bits; msda_zero_fill validates before
+    touching the device."""
     lib = _capi.lib()
     dims = _capi.MsdaDims(1, 4, 1, 32, 1, 1, 1)
-    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32, 2, None)
+    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32, 4, None)
     assert rc != 0 and "unknown flags" in _capi.last_error()
+    rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32,
+                           _capi.BWD_PREZEROED | _capi.BWD_DETERMINISTIC, None)
+    assert rc != 0 and "cannot be combined" in _capi.last_error()
+    # workspace of the deterministic mode: 256-byte header + an int64 image of grad_value
+    assert lib.msda_backward_workspace_bytes_ex(ctypes.byref(dims), _capi.F32, _capi.BWD_DETERMINISTIC) == 256 + 8 * 4 * 32
+    assert lib.msda_backward_workspace_bytes_ex(ctypes.byref(dims), _capi.BF16, 0) == lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.BF16)
     # the flag itself passes flag validation (the call then fails on the NULL tensors, not on the flag)
     rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32,
                            _capi.BWD_PREZEROED, None)

@@ -113,3 +113,54 @@ def test_workload_accounting_matches_survey():
     assert synthetic.WORKLOADS["C4DEC"].S == 22223
     shapes, start = synthetic.level_tensors(c2.levels)
     assert start.tolist() == [0, 10000, 12500, 13125]
+
+
+def test_export_graph_is_gather_based_like_the_reference():
+    """The ``is_tracing`` branch must trace to split / gather / arithmetic nodes only -- the reference avoids ``grid_sample``
+    on purpose (ms_deform_attn_func.py:99-102: its TensorRT tool chain has no GridSample) -- and compute the same numbers as
+    ``F.grid_sample`` (kept behind ``use_grid_sample=True``)."""
+    import torch
+
+    from aloception_oss_b200.functions import ms_deform_attn_core_pytorch
+    from aloception_oss_b200.synthetic import Workload, torch_inputs
+
+    w = Workload("exp", 2, ((6, 4), (3, 2), (1, 5)), 7, M=3, P=3, D=5)
+    x = torch_inputs(w, seed=3, loc_mode="wide", dtype=torch.float64)
+    shapes = [(int(h), int(wd)) for h, wd in x["shapes"]]
+    fn = lambda v, l, a: ms_deform_attn_core_pytorch(v, shapes, l, a)
+    traced = torch.jit.trace(fn, (x["value"], x["loc"], x["attn"]))
+    g = str(traced.graph)
+    assert "grid_sampler" not in g and "aten::gather" in g and "aten::pad" not in g and "constant_pad" not in g
+    a = fn(x["value"], x["loc"], x["attn"])
+    b = ms_deform_attn_core_pytorch(x["value"], shapes, x["loc"], x["attn"], use_grid_sample=True)
+    assert torch.allclose(a, b, rtol=1e-12, atol=1e-15)
+    assert torch.allclose(traced(x["value"], x["loc"], x["attn"]), a, rtol=0, atol=0)
+
+
+def test_level_size_check_is_keyed_on_the_live_tensor_not_on_its_address():
+    """A shapes tensor that passed ``sum(H*W) == Len_in`` is remembered, but a NEW tensor is always checked -- also when the
+    allocator hands it the address (and version counter) of a freed, validated one."""
+    import pytest
+    import torch
+
+    from aloception_oss_b200 import modules
+
+    m = modules.MSDeformAttn.__new__(modules.MSDeformAttn)  # the check needs no parameters (and no CUDA library)
+    good = torch.tensor([[4, 5], [2, 3]], dtype=torch.int32)
+    m._check_level_sizes(good, 26)
+    assert modules._VALIDATED_LEVELS[id(good)][0]() is good
+    m._check_level_sizes(good, 26)            # cached
+    with pytest.raises(AssertionError):
+        m._check_level_sizes(good, 27)        # same tensor, other Len_in: checked again
+    addr, key = good.data_ptr(), id(good)
+    del good
+    assert key not in modules._VALIDATED_LEVELS  # evicted with the tensor
+    for _ in range(8):  # whatever address the next tensors get (often the same block), inconsistent shapes raise
+        bad = torch.tensor([[4, 5], [2, 4]], dtype=torch.int32)
+        with pytest.raises(AssertionError):
+            m._check_level_sizes(bad, 26)
+        del bad
+    good2 = torch.tensor([[4, 5], [2, 3]], dtype=torch.int32)
+    good2[1, 1] = 4                           # in-place edit bumps the version counter
+    with pytest.raises(AssertionError):
+        m._check_level_sizes(good2, 26)

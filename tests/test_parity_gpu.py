@@ -503,3 +503,34 @@ def test_autograd_function_uses_the_early_zero_fill(cuda_device):
     with torch.no_grad():
         msda.MSDeformAttnFunction.apply(x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
     assert _capi.kernel_launch_count() == n0 + 1
+
+
+def test_module_traces_to_the_custom_op_node(cuda_device):
+    """torch.jit.trace of the module (default ``fused=True``) must record ``alonet_custom::ms_deform_attn_forward`` -- the
+    node the reference's TensorRT exporter replaces by its plugin (alonet/torch2trt/trt_exporter.py:41) -- not an opaque
+    ctypes call; eager execution keeps the fused kernels."""
+    torch.manual_seed(0)
+    dev = cuda_device
+    mod = msda.MSDeformAttn(256, 4, 8, 4).to(dev).eval()
+    levels = ((16, 20), (8, 10), (4, 5), (2, 3))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    q, src, ref = torch.randn(2, 50, 256, device=dev), torch.randn(2, S, 256, device=dev), torch.rand(2, 50, 4, 2, device=dev)
+    with torch.no_grad():
+        eager = mod(q, ref, src, shapes, start)
+        traced = torch.jit.trace(lambda a, b, c: mod(a, b, c, shapes, start), (q, ref, src), check_trace=False)
+        assert "alonet_custom::ms_deform_attn_forward" in str(traced.graph)
+        assert torch.allclose(traced(q, ref, src), eager, rtol=1e-4, atol=1e-5)
+
+
+def test_forward_unroll_knob_is_clamped_for_16bit_rows_of_16_channels(cuda_device):
+    """16-bit D = 16: a row is 2 lanes, the warp holds 16 lane groups; ``fwd_unroll = 4`` would address 64 samples per round."""
+    w = Workload("d16h", 2, ((7, 9), (3, 5)), 23, M=4, P=4, D=16)
+    x = torch_inputs(w, seed=61, loc_mode="wide")
+    xr = {k: (v.to(torch.bfloat16).float() if v.is_floating_point() else v) for k, v in x.items()}
+    want = oracle64(xr)[0]
+    for u in (0, 2, 4):
+        _capi.set_tuning("fwd_unroll", u)
+        got = run_op(xr, cuda_device, dtype=torch.bfloat16, need_grad=False)[0]
+        assert_close(got, want, 1e-2, 1e-2 * rms(want), f"out (fwd_unroll={u})")
