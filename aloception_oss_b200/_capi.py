@@ -21,6 +21,7 @@ ABI_VERSION = 1
 F32, BF16, F16, F64 = 0, 1, 2, 3
 BWD_PREZEROED = 1  # MSDA_BWD_PREZEROED
 BWD_DETERMINISTIC = 2  # MSDA_BWD_DETERMINISTIC
+FUSED_REF_F32 = 4  # MSDA_FUSED_REF_F32
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",
@@ -130,6 +131,8 @@ def lib() -> ctypes.CDLL:
     L.msda_fused_supported.argtypes = [dp, i, i]
     L.msda_fused_forward.restype = i
     L.msda_fused_forward.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, dp, i, vp]
+    L.msda_fused_forward_ex.restype = i
+    L.msda_fused_forward_ex.argtypes = [vp, vp, vp, vp, i, vp, vp, vp, dp, i, i, vp]
     L.msda_fused_backward.restype = i
     L.msda_fused_backward.argtypes = [vp] * 5 + [i] + [vp] * 7 + [sz, dp, i, i, vp]
     L.msda_set_tuning.restype = i

@@ -21,7 +21,7 @@ namespace {
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -362,6 +362,13 @@ int zero_fill(void* p, size_t bytes, cudaStream_t st) {
   return check_pdl_launch(e, "msda_backward(zero grad_value)");
 }
 
+// backward: all gather rounds before the fence?  Pays when the call is one wave behind a programmatic zero-fill (the gathers'
+// latency chains then hide behind the fill); measured in profiles/r2_sweep_bwd_two_pass.jsonl
+bool bwd_two_pass_auto(const msda_dims& d, bool pdl) {
+  (void)d; (void)pdl;
+  return false;
+}
+
 template <typename T, int D, int MC, bool FUSED = false, bool DET = false>
 int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
                    const void* attn, float* gv, void* gloc, void* gattn, const msda_dims& d, cudaStream_t st,
@@ -388,7 +395,10 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   const T* go_ = (const T*)go; const T* value_ = (const T*)value; const T* loc_ = (const T*)loc; const T* attn_ = (const T*)attn;
   T* gloc_ = (T*)gloc; T* gattn_ = (T*)gattn; const T* ref_ = (const T*)ref;
   const int S = d.spatial_size, M = d.num_heads, L = d.num_levels, P = d.num_point, QM = d.num_query * d.num_heads;
-  const int hm = l.head_major;
+  // knob "bwd_two_pass": 0 = auto, 1 = single pass (scatter of a round right behind its gather), 2 = gather pass / fence / scatter pass
+  const int tpk = g_bwd_two_pass.load(std::memory_order_relaxed);
+  const bool two_pass = tpk == 2 || (tpk == 0 && bwd_two_pass_auto(d, pdl));
+  const int hm = l.head_major | (two_pass ? 2 : 0);
   cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
   e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED, DET>, go_, value_, shapes, start, loc_, attn_, \
@@ -592,11 +602,16 @@ bool fused_shape_ok(const msda_dims& d, int dtype, int ref_dim) {
          (d.channels == 16 || d.channels == 32 || d.channels == 64 || d.channels == 128);
 }
 
+// `ref_dim` carries the MSDA_FUSED_REF_F32 request in bit 8 on its way to the kernels (fp32 reference points next to 16-bit
+// value / offsets / logits; for T = float the bit is dropped: nothing differs)
+constexpr int kRef32Bit = 0x100;
+
 template <typename T>
 int fused_forward_typed(const void* value, const int32_t* shapes, const int32_t* start, const void* ref, int ref_dim,
                         const void* off, const void* logits, void* out, const msda_dims& d, cudaStream_t st) {
+  if (sizeof(T) == 4) ref_dim &= ~kRef32Bit;
   if (!(aligned(value, 16) && aligned(out, 16) && aligned(off, 2 * sizeof(T)) && aligned(logits, sizeof(T)) &&
-        aligned(ref, sizeof(T))))
+        aligned(ref, (ref_dim & kRef32Bit) ? sizeof(float) : sizeof(T))))
     return kUnsupported;
 #define MSDA_CASE(DD)                                                                                         \
   case DD:                                                                                                    \
@@ -621,10 +636,11 @@ int fused_backward_typed(const void* go, const void* value, const int32_t* shape
                          int ref_dim, const void* off, const void* logits, void* grad_value, void* goff, void* glogits,
                          float* gref, void* workspace, const msda_dims& d, cudaStream_t st) {
   constexpr bool needs_ws = sizeof(T) != sizeof(float);
+  if (sizeof(T) == 4) ref_dim &= ~kRef32Bit;
   const size_t n_value = (size_t)d.batch * d.spatial_size * d.num_heads * d.channels;
   float* acc = needs_ws ? (float*)workspace : (float*)grad_value;
   if (!(aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) && aligned(off, 2 * sizeof(T)) &&
-        aligned(goff, 2 * sizeof(T)) && aligned(logits, sizeof(T)) && aligned(ref, sizeof(T))))
+        aligned(goff, 2 * sizeof(T)) && aligned(logits, sizeof(T)) && aligned(ref, (ref_dim & kRef32Bit) ? sizeof(float) : sizeof(T))))
     return kUnsupported;
   if (int rc = zero_fill(acc, n_value * sizeof(float), st)) return rc;
   int rc = kUnsupported;
@@ -691,6 +707,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "staged_warps")) return &g_staged_warps;
   if (!strcmp(name, "bwd_tile_mode")) return &g_bwd_tile_mode;
   if (!strcmp(name, "bwd_tile_ctas")) return &g_bwd_tile_ctas;
+  if (!strcmp(name, "bwd_two_pass")) return &g_bwd_two_pass;
   return nullptr;
 }
 
@@ -880,8 +897,16 @@ int msda_fused_supported(const msda_dims* dims, int dtype, int ref_dim) {
 int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
                        const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
                        void* output, const msda_dims* dims, int dtype, void* stream) {
+  return msda_fused_forward_ex(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits,
+                               output, dims, dtype, 0, stream);
+}
+
+int msda_fused_forward_ex(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                          const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                          void* output, const msda_dims* dims, int dtype, int flags, void* stream) {
   g_err[0] = 0;
   if (int rc = validate_dims(dims, dtype)) return rc;
+  if (flags & ~MSDA_FUSED_REF_F32) return fail("msda_fused_forward_ex: unknown flags 0x%x", flags);
   const msda_dims& d = *dims;
   if (!fused_shape_ok(d, dtype, ref_dim)) {
     fail("msda_fused_forward: shape/dtype outside the fused kernels (need L*P <= 32, D in {16,32,64,128}, no f64)");
@@ -893,6 +918,7 @@ int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const i
     return fail("NULL tensor pointer passed to msda_fused_forward");
   cudaStream_t st = (cudaStream_t)stream;
   int rc = kUnsupported;
+  if (flags & MSDA_FUSED_REF_F32) ref_dim |= kRef32Bit;
   switch (dtype) {
     case MSDA_F32: rc = fused_forward_typed<float>(value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, output, d, st); break;
 #ifndef MSDA_DEV_FAST
@@ -912,7 +938,7 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
                         const msda_dims* dims, int dtype, int flags, void* stream) {
   g_err[0] = 0;
   if (int rc = validate_dims(dims, dtype)) return rc;
-  if (flags != 0) return fail("flags must be 0");
+  if (flags & ~MSDA_FUSED_REF_F32) return fail("msda_fused_backward: unknown flags 0x%x", flags);
   const msda_dims& d = *dims;
   if (!fused_shape_ok(d, dtype, ref_dim)) {
     fail("msda_fused_backward: shape/dtype outside the fused kernels");
@@ -931,6 +957,7 @@ int msda_fused_backward(const void* grad_output, const void* value, const int32_
       !attn_logits || !grad_offsets || !grad_logits)
     return fail("NULL tensor pointer passed to msda_fused_backward");
   int rc = kUnsupported;
+  if (flags & MSDA_FUSED_REF_F32) ref_dim |= kRef32Bit;
   switch (dtype) {
     case MSDA_F32: rc = fused_backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, reference_points, ref_dim, sampling_offsets, attn_logits, grad_value, grad_offsets, grad_logits, grad_reference_points, workspace, d, st); break;
 #ifndef MSDA_DEV_FAST

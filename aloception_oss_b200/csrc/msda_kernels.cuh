@@ -268,6 +268,13 @@ __device__ __forceinline__ float load_s(const __half* p) {
   return __half2float(*reinterpret_cast<const __half*>(&h));
 }
 
+// Reference points of the fused operator: stored as T, or as fp32 next to 16-bit value / offsets / logits (`r32`; C-ABI flag
+// MSDA_FUSED_REF_F32) -- a bf16 reference point is quantised to 1/256 of the image, i.e. 0.4-0.8 px on a 100-200 px level.
+template <typename T>
+__device__ __forceinline__ float load_ref(const T* ref, long long i, bool r32) {
+  return r32 ? __ldg(reinterpret_cast<const float*>(ref) + i) : load_s(ref + i);
+}
+
 __device__ __forceinline__ void store_xy(float* p, float x, float y) { *reinterpret_cast<float2*>(p) = make_float2(x, y); }
 __device__ __forceinline__ void store_xy(__nv_bfloat16* p, float x, float y) {
   *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(x, y);
@@ -360,7 +367,7 @@ __device__ __forceinline__ float warp_sum(float v) {
 // `od` returns off / P (4-d) for the reference-point gradient.
 template <typename T>
 __device__ __forceinline__ SampleParams fused_params(const T* __restrict__ u_off, const T* __restrict__ u_logit,
-                                                     const T* __restrict__ ref_q, int RD,
+                                                     const T* __restrict__ ref, long long rq, int RD, bool r32,
                                                      const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                                                      int s, bool have, float inv_p, int P, int& l, float& odx, float& ody) {
   SampleParams p;
@@ -372,13 +379,13 @@ __device__ __forceinline__ SampleParams fused_params(const T* __restrict__ u_off
   p.H = __ldg(shapes + 2 * l);
   p.W = __ldg(shapes + 2 * l + 1);
   p.st = __ldg(start + l);
-  const float rx = load_s(ref_q + l * RD), ry = load_s(ref_q + l * RD + 1);
+  const float rx = load_ref(ref, rq + l * RD, r32), ry = load_ref(ref, rq + l * RD + 1, r32);
   if (RD == 2) {
     odx = 0.f; ody = 0.f;
     p.lx = __fadd_rn(rx, __fdiv_rn(ox, (float)p.W));
     p.ly = __fadd_rn(ry, __fdiv_rn(oy, (float)p.H));
   } else {
-    const float rw = load_s(ref_q + l * RD + 2), rh = load_s(ref_q + l * RD + 3);
+    const float rw = load_ref(ref, rq + l * RD + 2, r32), rh = load_ref(ref, rq + l * RD + 3, r32);
     odx = __fdiv_rn(ox, (float)P);
     ody = __fdiv_rn(oy, (float)P);
     p.lx = __fadd_rn(rx, __fmul_rn(__fmul_rn(odx, rw), 0.5f));
@@ -408,18 +415,18 @@ __device__ __forceinline__ LevelMeta load_level_meta(const int32_t* __restrict__
 
 template <typename T, bool FUSED>
 __device__ __forceinline__ RawSample load_raw(const T* __restrict__ u_loc, const T* __restrict__ u_att,
-                                              const T* __restrict__ ref_q, int RD, int s, bool have, int l) {
+                                              const T* __restrict__ ref, long long rq, int RD, bool r32, int s, bool have, int l) {
   RawSample r;
   const int si = have ? s : 0;
   load_xy(u_loc + 2 * si, r.x, r.y);
   r.rx = r.ry = r.rw = r.rh = 0.f;
   if constexpr (FUSED) {
     r.a = have ? load_s(u_att + si) : -INFINITY;
-    r.rx = load_s(ref_q + l * RD);
-    r.ry = load_s(ref_q + l * RD + 1);
+    r.rx = load_ref(ref, rq + l * RD, r32);
+    r.ry = load_ref(ref, rq + l * RD + 1, r32);
     if (RD != 2) {
-      r.rw = load_s(ref_q + l * RD + 2);
-      r.rh = load_s(ref_q + l * RD + 3);
+      r.rw = load_ref(ref, rq + l * RD + 2, r32);
+      r.rh = load_ref(ref, rq + l * RD + 3, r32);
     }
   } else {
     r.a = load_s(u_att + si);
@@ -699,8 +706,10 @@ __device__ __forceinline__ void
 msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
               const int32_t* __restrict__ start, const T* __restrict__ loc,
               const T* __restrict__ attn, T* __restrict__ out,
-              int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m,
+              int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int b, int uq, int m,
               int spec_on = 0) {
+  const int RD = RDf & 0xff;            // last dim of the reference points (2 or 4)
+  const bool r32 = (RDf & 0x100) != 0;  // ... which are fp32 although T is a 16-bit type
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   static_assert(D % VEC == 0 && LPR >= 1 && LPR <= 32 && (LPR & (LPR - 1)) == 0, "unsupported D for the vector path");
@@ -730,7 +739,7 @@ msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
       if constexpr (FUSED) {
         int l;
         float odx, ody;
-        sp = fused_params<T>(u_loc, u_att, ref + ((long long)b * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, l, odx, ody);
+        sp = fused_params<T>(u_loc, u_att, ref, ((long long)b * (QM / M) + uq / M) * (L * RD), RD, r32, shapes, start, lane, have, inv_p, P, l, odx, ody);
       } else {
         sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
       }
@@ -764,8 +773,8 @@ template <typename T, int D, int MC, bool FUSED, bool SR>
 __device__ __noinline__ void
 msda_fwd_unit_flagged(const T* __restrict__ value, const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                       const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
-                      int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int b, int uq, int m) {
-  msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b, uq, m, 0);
+                      int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int b, int uq, int m) {
+  msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, b, uq, m, 0);
 }
 
 // grid: x = units of one image (one warp each), y = image
@@ -774,11 +783,11 @@ __global__ void __launch_bounds__(MSDA_MAX_THREADS, U == 1 ? MSDA_FWD_MIN_CTAS :
 msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                    const int32_t* __restrict__ start, const T* __restrict__ loc,
                    const T* __restrict__ attn, T* __restrict__ out,
-                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int head_major, int spec_on) {
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int head_major, int spec_on) {
   const int M = MC > 0 ? MC : Mrt;
   int uq, m;  // unit inside image blockIdx.y, its head
   if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
-  msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, (int)blockIdx.y, uq, m, spec_on);
+  msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, (int)blockIdx.y, uq, m, spec_on);
 }
 
 // PATCH-ORDERED forward for pixel-aligned queries (encoder self-attention: Lq == S, query i is pixel i of the pyramid
@@ -797,9 +806,11 @@ __global__ void __launch_bounds__(MSDA_PATCH_MAX_THREADS, MINB)
 msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                       const int32_t* __restrict__ start, const T* __restrict__ loc,
                       const T* __restrict__ attn, T* __restrict__ out,
-                      int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD, int PX, int spec_on) {
+                      int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int PX, int spec_on) {
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
+  const int RD = RDf & 0xff;
+  const bool r32 = (RDf & 0x100) != 0;
   const int M = MC > 0 ? MC : Mrt;
   const int MD = M * D;
   const int PY = blockDim.x >> 5;
@@ -843,12 +854,12 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
     // walk the row: the loads of unit i + 1 are issued before the gathers of unit i (needs L * P <= 32: host-checked)
     const T* __restrict__ vb = value + (long long)b * S * MD + (m * D + cl * VEC);
     long long u = (long long)b * QM + (long long)q0 * M + m;
-    RawSample raw = load_raw<T, FUSED>(loc + u * (LP * 2), attn + u * LP, ref + ((long long)b * Lq + q0) * (L * RD), RD, lane, have, lm.l);
+    RawSample raw = load_raw<T, FUSED>(loc + u * (LP * 2), attn + u * LP, ref, ((long long)b * Lq + q0) * (L * RD), RD, r32, lane, have, lm.l);
     for (int i = 0; i < n_q; ++i) {
       const RawSample cur = raw;
       if (i + 1 < n_q) {
         const long long un = u + M;
-        raw = load_raw<T, FUSED>(loc + un * (LP * 2), attn + un * LP, ref + ((long long)b * Lq + q0 + i + 1) * (L * RD), RD, lane, have, lm.l);
+        raw = load_raw<T, FUSED>(loc + un * (LP * 2), attn + un * LP, ref, ((long long)b * Lq + q0 + i + 1) * (L * RD), RD, r32, lane, have, lm.l);
       }
       const SampleParams sp = params_from_raw<FUSED>(cur, lm, RD, P, have);
       constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
@@ -869,7 +880,7 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
         if (done && owner) store_vals<T, N_OUT>(out + u * D + cl * VEC + first, o);
       }
       if (!done)
-        msda_fwd_unit_flagged<T, D, MC, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b,
+        msda_fwd_unit_flagged<T, D, MC, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, b,
                                                    (int)(u - (long long)b * QM), m);
       u += M;
     }
@@ -879,7 +890,7 @@ msda_fwd_patch_kernel(const T* __restrict__ value, const int32_t* __restrict__ s
   for (long long t = (long long)blockIdx.x * PY + w; t < tail; t += (long long)gridDim.x * PY) {
     const int bm = (int)(t % NM);
     const int q = pixels + (int)(t / NM);
-    msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, bm / M, q * M + bm % M, bm % M, spec_on);
+    msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, bm / M, q * M + bm % M, bm % M, spec_on);
   }
 }
 
@@ -936,8 +947,10 @@ __global__ void __launch_bounds__(TPB, MINB)
 msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
                        const int32_t* __restrict__ start, const T* __restrict__ loc,
                        const T* __restrict__ attn, T* __restrict__ out,
-                       int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
+                       int N, int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf,
                        int tile_rows, int spec_on) {
+  const int RD = RDf & 0xff;
+  const bool r32 = (RDf & 0x100) != 0;
   constexpr int VEC = Vec16<T>::N;
   constexpr int LPR = D / VEC;
   constexpr int G = 32 / LPR;
@@ -994,14 +1007,14 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
   uint32_t parity = 0;
 
   // pointers of my warp's unit of item (bm, c); they advance by constants while the item stays in the same (image, head)
-  const T* p_loc; const T* p_att; const T* p_ref = nullptr; T* p_out;
+  const T* p_loc; const T* p_att; long long p_ref = 0; T* p_out;  // p_ref: element index into the reference points
   auto seek = [&](int bm_, int c_) {
     const int q = c_ * nw + w, b = bm_ / M, m = bm_ % M;
     const long long u = (long long)b * QM + (long long)q * M + m;
     p_loc = loc + (u * LP + slane) * 2;
     p_att = attn + u * LP + slane;
     p_out = out + u * D;
-    if constexpr (FUSED) p_ref = ref + (((long long)b * Lq + q) * L + lm.l) * RD;
+    if constexpr (FUSED) p_ref = (((long long)b * Lq + q) * L + lm.l) * RD;
   };
   const int d_att = nw * M * LP, d_out = nw * M * D, d_ref = nw * L * RD;
   auto fetch = [&]() {
@@ -1010,9 +1023,9 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
     r.rx = r.ry = r.rw = r.rh = 0.f;
     if constexpr (FUSED) {
       r.a = have ? load_s(p_att) : -INFINITY;
-      r.rx = load_s(p_ref);
-      r.ry = load_s(p_ref + 1);
-      if (RD != 2) { r.rw = load_s(p_ref + 2); r.rh = load_s(p_ref + 3); }
+      r.rx = load_ref(ref, p_ref, r32);
+      r.ry = load_ref(ref, p_ref + 1, r32);
+      if (RD != 2) { r.rw = load_ref(ref, p_ref + 2, r32); r.rh = load_ref(ref, p_ref + 3, r32); }
     } else {
       r.a = load_s(p_att);
     }
@@ -1113,7 +1126,7 @@ msda_fwd_staged_kernel(const T* __restrict__ value, const int32_t* __restrict__ 
       if (done && owner) store_vals<T, N_OUT>(o_cur + cl * VEC + first, o);
     }
     if (!done)  // a level narrower than 2 pixels, or non-finite sums: the exact zero-line path, out of line
-      msda_fwd_unit_flagged<T, D, MC, FUSED, true>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RD, b, q * M + m, m);
+      msda_fwd_unit_flagged<T, D, MC, FUSED, true>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, b, q * M + m, m);
   }
 }
 
@@ -1184,8 +1197,10 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                    const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                    const T* __restrict__ loc, const T* __restrict__ attn, float* __restrict__ gv,
                    T* __restrict__ gloc, T* __restrict__ gattn,
-                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RD,
+                   int S, int Mrt, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf,
                    float* __restrict__ gref, int head_major, const unsigned* __restrict__ det_hdr = nullptr) {
+  const int RD = RDf & 0xff;
+  const bool r32 = (RDf & 0x100) != 0;
   using IO = VecIO<T, BwdGranule<T>::VB>;
   constexpr int VEC = IO::N;
   constexpr int LPR = D / VEC;
@@ -1195,8 +1210,9 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   const int M = MC > 0 ? MC : Mrt;
   const int MD = M * D;
   const int lane = threadIdx.x & 31;
+  const bool two_pass = (head_major & 2) != 0;  // bit 1 of the scheduling word: gather pass, fence, scatter pass
   int uq, m;
-  if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform (an exited warp needs no fence)
+  if (!unit_of_warp(M, QM, head_major & 1, uq, m)) return;  // warp-uniform (an exited warp needs no fence)
   const int g = lane / LPR, cl = lane % LPR;
   const int LP = L * P;
   const long long u = (long long)blockIdx.y * QM + uq;
@@ -1224,7 +1240,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
     float odx = 0.f, ody = 0.f;
     const bool have = base + lane < LP;
     if constexpr (FUSED) {
-      sp = fused_params<T>(u_loc, u_att, ref + ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, shapes, start, lane, have, inv_p, P, lvl, odx, ody);
+      sp = fused_params<T>(u_loc, u_att, ref, ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, r32, shapes, start, lane, have, inv_p, P, lvl, odx, ody);
     } else {
       sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
     }
@@ -1234,8 +1250,8 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
     const float w00 = ge.hy * ge.hx * a, w01 = ge.hy * ge.lx * a, w10 = ge.ly * ge.hx * a, w11 = ge.ly * ge.lx * a;
     const int cnt = min(32, LP - base);
     float r00 = 0.f, r01 = 0.f, r10 = 0.f, r11 = 0.f;  // <grad_out, tap> of MY sample, from the group that gathered it
-    for (int k0 = 0; k0 < cnt; k0 += G * U) {
-      int off[U], rsf[U];
+    // which samples the lane groups handle in round k0; true if every tap of the round is valid (warp-uniform)
+    auto round_index = [&](int k0, int (&off)[U], int (&rsf)[U]) -> bool {
       bool full = true;
 #pragma unroll
       for (int j = 0; j < U; ++j) {
@@ -1245,7 +1261,10 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         if (src >= cnt) rsf[j] = 0;  // shfl wraps modulo 32: a lane group past the end must not gather / scatter
         full = full && ((rsf[j] & 15) == 15);
       }
-      const bool all_ok = __all_sync(0xffffffffu, full);
+      return __all_sync(0xffffffffu, full);
+    };
+    // gather half of a round: <grad_out, tap> of the round's samples, returned to the lanes that own them
+    auto gather_round = [&](int k0, const int (&off)[U], const int (&rsf)[U], bool all_ok) {
       typename IO::Raw v[U][4];
       if (all_ok) {  // loads duplicated per branch: here the x+1 taps are immediate offsets of the x taps
 #pragma unroll
@@ -1288,11 +1307,10 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
         const float t11 = __shfl_sync(0xffffffffu, d[3], from);
         if (rel >= 0 && rel < G) { r00 = t00; r01 = t01; r10 = t10; r11 = t11; }
       }
-      // ---- scatter: needs the zero-fill of grad_value (previous kernel) complete and visible ----
-      if (!fenced) {
-        pdl_wait();
-        fenced = true;
-      }
+    };
+    // scatter half of a round: needs the zero-fill of grad_value (previous kernel) complete and visible; it does not
+    // depend on the gathered taps at all (contribution = weight * attention * grad_out)
+    auto scatter_round = [&](int k0, const int (&off)[U], const int (&rsf)[U]) {
 #pragma unroll
       for (int j = 0; j < U; ++j) {
         const int src = k0 + j * G + g;
@@ -1313,56 +1331,90 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                 atomicAdd(gp[t] + i, (unsigned long long)__float2ll_rn(__fmul_rn(__fmul_rn(__fmul_rn(w[t], go[i]), det_s1), det_s2)));
             }
         } else {
-        float* g0 = gb + off[j];
-        float* g1 = g0 + (rsf[j] >> 4);
-        float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
+          float* g0 = gb + off[j];
+          float* g1 = g0 + (rsf[j] >> 4);
+          float* gp[4] = {g0, g0 + MD, g1, g1 + MD};
 #pragma unroll
-        for (int t = 0; t < 4; ++t)
-          if (rsf[j] & (1 << t)) {
+          for (int t = 0; t < 4; ++t)
+            if (rsf[j] & (1 << t)) {
 #pragma unroll
-            for (int i = 0; i < VEC; i += 4) {
-              const float2 lo = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i], go[i + 1]));
-              const float2 hi = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i + 2], go[i + 3]));
-              red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
+              for (int i = 0; i < VEC; i += 4) {
+                const float2 lo = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i], go[i + 1]));
+                const float2 hi = __fmul2_rn(make_float2(w[t], w[t]), make_float2(go[i + 2], go[i + 3]));
+                red_add_v4(gp[t] + i, lo.x, lo.y, hi.x, hi.y);
+              }
+            }
+        }
+      }
+    };
+    // grad_attn / grad_loc of MY sample from the four returned dot products
+    auto epilogue = [&]() {
+      const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
+      const float bot = ge.hx * r10 + ge.lx * r11;  // ... on row y0 + 1
+      const float g_a = ge.hy * top + ge.ly * bot;                                  // d out / d A_i
+      const float g_lx = (float)W * a * (ge.hy * (r01 - r00) + ge.ly * (r11 - r10));  // d out / d loc_x
+      const float g_ly = (float)H * a * (bot - top);                                  // d out / d loc_y
+      const long long sidx = u * LP + base + lane;
+      if constexpr (!FUSED) {
+        if (have) {  // coalesced: 32 consecutive samples of the unit
+          gattn[sidx] = from_acc<T>(g_a);
+          store_xy(gloc + 2 * sidx, g_lx, g_ly);
+        }
+      } else {
+        // softmax backward over the unit's samples:  g_logit_i = A_i * (g_A_i - sum_j A_j g_A_j)
+        const float dot = warp_sum(have ? a * g_a : 0.f);
+        if (have) {
+          gattn[sidx] = from_acc<T>(a * (g_a - dot));
+          const long long rbase = (((long long)blockIdx.y * (QM / M) + uq / M) * L + lvl) * RD;
+          if (RD == 2) {
+            store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx, (float)W), __fdiv_rn(g_ly, (float)H));
+            if (gref != nullptr) {
+              atomicAdd(gref + rbase, g_lx);
+              atomicAdd(gref + rbase + 1, g_ly);
+            }
+          } else {
+            const float rw = load_ref(ref, rbase + 2, r32), rh = load_ref(ref, rbase + 3, r32);
+            store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx * 0.5f * rw, (float)P), __fdiv_rn(g_ly * 0.5f * rh, (float)P));
+            if (gref != nullptr) {
+              atomicAdd(gref + rbase, g_lx);
+              atomicAdd(gref + rbase + 1, g_ly);
+              atomicAdd(gref + rbase + 2, g_lx * 0.5f * odx);
+              atomicAdd(gref + rbase + 3, g_ly * 0.5f * ody);
             }
           }
         }
       }
-    }
-    const float top = ge.hx * r00 + ge.lx * r01;  // interpolated along x on row y0
-    const float bot = ge.hx * r10 + ge.lx * r11;  // ... on row y0 + 1
-    const float g_a = ge.hy * top + ge.ly * bot;                                  // d out / d A_i
-    const float g_lx = (float)W * a * (ge.hy * (r01 - r00) + ge.ly * (r11 - r10));  // d out / d loc_x
-    const float g_ly = (float)H * a * (bot - top);                                  // d out / d loc_y
-    const long long sidx = u * LP + base + lane;
-    if constexpr (!FUSED) {
-      if (have) {  // coalesced: 32 consecutive samples of the unit
-        gattn[sidx] = from_acc<T>(g_a);
-        store_xy(gloc + 2 * sidx, g_lx, g_ly);
+    };
+    if (two_pass) {
+      // every gather round (a dependent-latency chain per round) runs while the zero-fill is still in flight; behind the
+      // fence only the reds remain
+      for (int k0 = 0; k0 < cnt; k0 += G * U) {
+        int off[U], rsf[U];
+        const bool all_ok = round_index(k0, off, rsf);
+        gather_round(k0, off, rsf, all_ok);
+      }
+      epilogue();
+      if (!fenced) {
+        pdl_wait();
+        fenced = true;
+      }
+      for (int k0 = 0; k0 < cnt; k0 += G * U) {
+        int off[U], rsf[U];
+        round_index(k0, off, rsf);
+        scatter_round(k0, off, rsf);
       }
     } else {
-      // softmax backward over the unit's samples:  g_logit_i = A_i * (g_A_i - sum_j A_j g_A_j)
-      const float dot = warp_sum(have ? a * g_a : 0.f);
-      if (have) {
-        gattn[sidx] = from_acc<T>(a * (g_a - dot));
-        const long long rbase = (((long long)blockIdx.y * (QM / M) + uq / M) * L + lvl) * RD;
-        if (RD == 2) {
-          store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx, (float)W), __fdiv_rn(g_ly, (float)H));
-          if (gref != nullptr) {
-            atomicAdd(gref + rbase, g_lx);
-            atomicAdd(gref + rbase + 1, g_ly);
-          }
-        } else {
-          const float rw = load_s(ref + rbase + 2), rh = load_s(ref + rbase + 3);
-          store_xy(gloc + 2 * sidx, __fdiv_rn(g_lx * 0.5f * rw, (float)P), __fdiv_rn(g_ly * 0.5f * rh, (float)P));
-          if (gref != nullptr) {
-            atomicAdd(gref + rbase, g_lx);
-            atomicAdd(gref + rbase + 1, g_ly);
-            atomicAdd(gref + rbase + 2, g_lx * 0.5f * odx);
-            atomicAdd(gref + rbase + 3, g_ly * 0.5f * ody);
-          }
+      for (int k0 = 0; k0 < cnt; k0 += G * U) {
+        int off[U], rsf[U];
+        const bool all_ok = round_index(k0, off, rsf);
+        gather_round(k0, off, rsf, all_ok);
+        if (!fenced) {
+          pdl_wait();
+          fenced = true;
         }
+        scatter_round(k0, off, rsf);
       }
+      epilogue();
     }
   }
 }

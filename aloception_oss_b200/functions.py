@@ -304,23 +304,39 @@ def fused_supported(value, spatial_shapes, reference_points, sampling_offsets, a
     return bool(_capi.lib().msda_fused_supported(ctypes.byref(dims), _DTYPES[value.dtype], rd))
 
 
+def _ref_flag(value, reference_points):
+    """fp32 reference points next to 16-bit value / offsets / logits (torch.autocast): MSDA_FUSED_REF_F32."""
+    if reference_points.dtype == value.dtype:
+        return 0
+    if reference_points.dtype == torch.float32 and value.dtype in (torch.bfloat16, torch.float16):
+        return _capi.FUSED_REF_F32
+    raise RuntimeError(f"reference_points must have value's dtype ({value.dtype}) or be float32 next to 16-bit tensors, "
+                       f"got {reference_points.dtype}")
+
+
 def ms_deform_attn_fused_forward(value, spatial_shapes, level_start_index, reference_points, sampling_offsets,
                                  attn_logits):
-    """(N,S,M,D), (L,2), (L,), (N,Lq,L,2|4), raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P) -> (N, Lq, M*D)."""
+    """(N,S,M,D), (L,2), (L,), (N,Lq,L,2|4), raw offsets (N,Lq,M,L,P,2), raw logits (N,Lq,M,L*P) -> (N, Lq, M*D).
+
+    ``reference_points`` may stay float32 when the other tensors are bfloat16 / float16 (include/msda_b200.h,
+    MSDA_FUSED_REF_F32): the sampling locations are then computed from the exact points."""
     named = [("value", value), ("spatial_shapes", spatial_shapes), ("level_start_index", level_start_index),
              ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits)]
     _check_inputs(named)
-    for name, t in named[3:]:
+    for name, t in named[4:]:
         if t.dtype != value.dtype or t.device != value.device:
             raise RuntimeError(f"{name} must have value's dtype and device")
+    if reference_points.device != value.device:
+        raise RuntimeError("reference_points must be on value's device")
+    flags = _ref_flag(value, reference_points)
     dims, rd = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
     out = torch.empty((dims.batch, dims.num_query, dims.num_heads * dims.channels), dtype=value.dtype, device=value.device)
     with _on_device(value) as stream:
-        rc = _capi.lib().msda_fused_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
-                                            _ptr(sampling_offsets), _ptr(attn_logits), _ptr(out), ctypes.byref(dims),
-                                            _DTYPES[value.dtype], stream)
+        rc = _capi.lib().msda_fused_forward_ex(_ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
+                                               _ptr(sampling_offsets), _ptr(attn_logits), _ptr(out), ctypes.byref(dims),
+                                               _DTYPES[value.dtype], flags, stream)
     if rc != 0:
         raise RuntimeError("msda_fused_forward failed: " + _capi.last_error())
     return out
@@ -333,6 +349,7 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
              ("reference_points", reference_points), ("sampling_offsets", sampling_offsets), ("attn_logits", attn_logits),
              ("grad_output", grad_output)]
     _check_inputs(named)
+    flags = _ref_flag(value, reference_points)
     dims, rd = _fused_dims(value, spatial_shapes, reference_points, sampling_offsets, attn_logits)
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
@@ -348,12 +365,12 @@ def ms_deform_attn_fused_backward(value, spatial_shapes, level_start_index, refe
         rc = L.msda_fused_backward(_ptr(grad_output), _ptr(value), _ptr(shapes), _ptr(start), _ptr(reference_points), rd,
                                    _ptr(sampling_offsets), _ptr(attn_logits), _ptr(grad_value), _ptr(grad_off),
                                    _ptr(grad_logits), _ptr(grad_ref) if grad_ref is not None else None,
-                                   _ptr(ws) if ws is not None else None, ws_bytes, ctypes.byref(dims), dt, 0,
+                                   _ptr(ws) if ws is not None else None, ws_bytes, ctypes.byref(dims), dt, flags,
                                    stream)
     if rc != 0:
         raise RuntimeError("msda_fused_backward failed: " + _capi.last_error())
-    if grad_ref is not None and grad_ref.dtype != value.dtype:
-        grad_ref = grad_ref.to(value.dtype)
+    if grad_ref is not None and grad_ref.dtype != reference_points.dtype:
+        grad_ref = grad_ref.to(reference_points.dtype)
     return grad_value, grad_ref, grad_off, grad_logits
 
 

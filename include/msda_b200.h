@@ -134,11 +134,19 @@ int msda_forward_host(const void* value, const int32_t* spatial_shapes, const in
  * caller composes the unfused operator.
  * msda_fused_backward: grad_offsets / grad_logits are gradients w.r.t. the raw inputs; grad_reference_points
  * (fp32, (N, Lq, L, ref_dim), ZEROED BY THE CALLER, may be NULL) is accumulated with reds.
+ * MSDA_FUSED_REF_F32 (flag of msda_fused_forward_ex / msda_fused_backward): reference_points are fp32 although `dtype` is a
+ * 16-bit type -- what torch.autocast produces (the Linear layers emit bf16, the reference points stay fp32).  Rounding a
+ * reference point to bf16 moves the sample by up to 1/256 of the image (0.4-0.8 px on a 100-200 px level); with the flag
+ * the location arithmetic starts from the exact fp32 point.  Ignored for MSDA_F32.
  */
+#define MSDA_FUSED_REF_F32 4
 int msda_fused_supported(const msda_dims* dims, int dtype, int ref_dim);
 int msda_fused_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
                        const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
                        void* output, const msda_dims* dims, int dtype, void* stream);
+int msda_fused_forward_ex(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                          const void* reference_points, int ref_dim, const void* sampling_offsets, const void* attn_logits,
+                          void* output, const msda_dims* dims, int dtype, int flags, void* stream);
 int msda_fused_backward(const void* grad_output, const void* value, const int32_t* spatial_shapes,
                         const int32_t* level_start_index, const void* reference_points, int ref_dim,
                         const void* sampling_offsets, const void* attn_logits, void* grad_value, void* grad_offsets,
@@ -190,6 +198,8 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *                      summed in registers, ONE red per destination and tile; fp32, D = 32, P = 4, L <= 16, S <= 2^19,
  *                      16-byte aligned tensors; other problems keep the unit-ordered kernel)
  *   "bwd_tile_ctas"    0=2, else persistent CTAs per SM of the tile-binned backward (1 or 2)
+ *   "bwd_two_pass"     0=auto, 1=unit-ordered backward scatters each round right behind its gather, 2=all gather rounds, then
+ *                      the fence behind the zero-fill, then all scatter rounds
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

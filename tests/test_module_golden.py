@@ -110,3 +110,83 @@ def test_fused_function_equals_unfused_composition(ref_dim, dtype, rtol, cuda_de
     assert_close(f(out1), f(out2), rtol, rtol * rms(f(out2)), "out")
     for a, b, n in ((v1, v2, "grad_value"), (r1, r2, "grad_ref"), (o1, o2, "grad_offsets"), (l1, l2, "grad_logits")):
         assert_close(f(a.grad), f(b.grad), rtol, rtol * rms(f(b.grad)), n)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("ref_dim", [2, 4])
+def test_fused_function_keeps_fp32_reference_points_next_to_bf16_tensors(ref_dim, cuda_device):
+    """torch.autocast leaves the reference points in fp32 while value / offsets / logits are bf16.  With MSDA_FUSED_REF_F32
+    the kernel starts the location arithmetic from the EXACT points: the result must agree with the fp32 composition on the
+    exact points, and be clearly closer to it than what rounding the points to bf16 (1/256 of the image = 0.65 px on the
+    167-px level) gives."""
+    msda.load_ops()
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(6)
+    levels = ((100, 167), (50, 84), (25, 42), (13, 21))
+    N, Lq, M, D, L, P = 2, 300, 8, 32, 4, 4
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    rnd = lambda *s: torch.rand(*s, device=dev, generator=g)
+    value = (rnd(N, S, M, D) - 0.5).to(torch.bfloat16)
+    ref = rnd(N, Lq, L, 2) * 0.9 + 0.05
+    if ref_dim == 4:
+        ref = torch.cat([ref, rnd(N, Lq, L, 2) * 0.3], -1)
+    off = ((rnd(N, Lq, M, L, P, 2) - 0.5) * 8).to(torch.bfloat16)
+    logits = ((rnd(N, Lq, M, L * P) - 0.5) * 4).to(torch.bfloat16)
+    go = (rnd(N, Lq, M * D) - 0.5).to(torch.bfloat16)
+
+    def run(ref_in):
+        v, r, o, l = [t.detach().clone().requires_grad_(True) for t in (value, ref_in, off, logits)]
+        out = msda.MSDeformAttnFusedFunction.apply(v, shapes, start, r, o, l)
+        out.backward(go)
+        return out, v.grad, r.grad, o.grad, l.grad
+
+    got = run(ref)                        # fp32 points, bf16 everything else
+    old = run(ref.to(torch.bfloat16))     # what the module did before: points rounded to bf16
+    assert got[2].dtype == torch.float32 and old[2].dtype == torch.bfloat16
+    # fp32 composition on the exact points (value / offsets / logits as stored, i.e. bf16-rounded)
+    v2, r2, o2, l2 = [t.float().detach().requires_grad_(True) for t in (value, ref, off, logits)]
+    attn = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = r2[:, :, None, :, None, :] + o2 / norm[None, None, None, :, None, :]
+    else:
+        loc = r2[:, :, None, :, None, :2] + o2 / P * r2[:, :, None, :, None, 2:] * 0.5
+    out2 = msda.MSDeformAttnFunction.apply(v2, shapes, start, loc.contiguous(), attn.contiguous(), 64)
+    out2.backward(go.float())
+    f = lambda t: t.detach().double().cpu().numpy()
+    want = [f(out2), f(v2.grad), f(r2.grad), f(o2.grad), f(l2.grad)]
+    names = ("out", "grad_value", "grad_ref", "grad_offsets", "grad_logits")
+    for a, w, n in zip(got, want, names):
+        assert_close(f(a), w, 2e-2, 2e-2 * rms(w), n)
+    err_new = np.sqrt(((f(got[0]) - want[0]) ** 2).mean())
+    err_old = np.sqrt(((f(old[0]) - want[0]) ** 2).mean())
+    assert err_new < 0.25 * err_old, (err_new, err_old)
+
+
+@pytest.mark.gpu
+def test_module_under_autocast_tracks_the_fp32_module(cuda_device):
+    """MSDeformAttn under torch.autocast(bf16) (fused path, fp32 reference points kept) vs the same module in fp32."""
+    msda.load_ops()
+    dev = cuda_device
+    torch.manual_seed(0)
+    mod = msda.MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    levels = ((100, 167), (50, 84), (25, 42), (13, 21))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    q, src, ref = torch.randn(2, 300, 256, device=dev), torch.randn(2, S, 256, device=dev), torch.rand(2, 300, 4, 2, device=dev)
+    with torch.no_grad():
+        want = mod(q, ref, src, shapes, start)
+        with torch.autocast("cuda", dtype=torch.bfloat16):
+            got = mod(q, ref, src, shapes, start)
+            old = mod(q, ref.to(torch.bfloat16), src, shapes, start)
+    e_new = (got.float() - want).pow(2).mean().sqrt().item()
+    e_old = (old.float() - want).pow(2).mean().sqrt().item()
+    scale = want.pow(2).mean().sqrt().item()
+    assert e_new < 3e-2 * scale, (e_new, scale)
+    assert e_new < e_old, (e_new, e_old)

@@ -24,7 +24,7 @@ def _ops(cuda_device):
     msda.load_ops()
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
               "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
-              "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas"):
+              "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas", "bwd_two_pass"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -131,7 +131,8 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
                                       ("bwd_unroll", 4), ("warps_per_block", 3), ("warps_per_block", 8), ("head_major", 2),
                                       ("smem_records", 1), ("smem_records", 2), ("patch_mode", 2),
-                                      ("staged_mode", 2), ("zero_mode", 2), ("zero_threads", 64), ("spec_mode", 1)])
+                                      ("staged_mode", 2), ("zero_mode", 2), ("zero_threads", 64), ("spec_mode", 1),
+                                      ("bwd_two_pass", 2)])
 def test_kernel_variants_agree(knob, val, no_pdl, w, cuda_device):
     x = torch_inputs(w, seed=16, loc_mode="wide")
     want = oracle64(x)
@@ -517,10 +518,18 @@ def test_module_traces_to_the_custom_op_node(cuda_device):
     shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
     start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
     q, src, ref = torch.randn(2, 50, 256, device=dev), torch.randn(2, S, 256, device=dev), torch.rand(2, 50, 4, 2, device=dev)
+    class Wrap(torch.nn.Module):  # (tracing a closure over a module cannot embed its parameters)
+        def __init__(self):
+            super().__init__()
+            self.mod = mod
+
+        def forward(self, a, b, c):
+            return self.mod(a, b, c, shapes, start)
+
     with torch.no_grad():
         eager = mod(q, ref, src, shapes, start)
-        traced = torch.jit.trace(lambda a, b, c: mod(a, b, c, shapes, start), (q, ref, src), check_trace=False)
-        assert "alonet_custom::ms_deform_attn_forward" in str(traced.graph)
+        traced = torch.jit.trace(Wrap(), (q, ref, src), check_trace=False)
+        assert "alonet_custom::ms_deform_attn_forward" in str(traced.inlined_graph)
         assert torch.allclose(traced(q, ref, src), eager, rtol=1e-4, atol=1e-5)
 
 
