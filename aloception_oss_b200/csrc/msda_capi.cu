@@ -416,9 +416,10 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
 
 // Tile-binned backward (msda_bwd_tile.cuh): fp32, D = 32, P = 4.  knob "bwd_tile_mode": 0 = auto, 1 = off, 2 = on.
 // Auto is OFF: measured on the B200 (profiles/r2_bwd_tile_*.jsonl, r2_ncu_bwd_tile.md) the kernel issues 5 x fewer reds and
-// fetches each window row once per tile, but it is instruction-bound (13 warp instructions per tap against 11 for the
-// unit-ordered kernel, which is bound by the red rate instead): ENC 331 us vs 266 us, C5ENC 497 vs 453 us.  It stays as a
-// tested schedule of the same function (any sampling locations, any Lq) for callers that want fewer atomics.
+// fetches each window row once per tile, but it is instruction-bound (11.4 warp instructions per tap, as many as the
+// unit-ordered kernel, which is bound by the red rate instead, at a lower issue rate): ENC 309 us vs 265 us, C5ENC 473 vs 451,
+// C4ENC 906 vs 898; random locations 518 vs 292.  It stays as a tested schedule of the same function (any sampling locations,
+// any Lq) for callers that want fewer atomics.
 constexpr int kTileTPQ = 2, kTileMaxB = 2048;
 
 bool bwd_tile_shape_ok(const msda_dims& d) {

@@ -46,6 +46,7 @@ def parse_args():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-bind", action="store_true", help="do not pin the process to the GPU's NUMA-local CPUs")
     ap.add_argument("--extra", action="store_true", help="also time the other COCO shapes (reported under 'extra')")
+    ap.add_argument("--no-north-star", action="store_true", help="skip the forward-only timing of the 800x1333 / 300-query shapes")
     return ap.parse_args()
 
 
@@ -404,6 +405,8 @@ def main():
     extra = {}
     if args.extra and rank == 0:
         extra = run_extra(torch, msda, _capi, dev, tdt, elt, peak)
+    # BASELINE.json's target is quoted on the 800x1333 pyramid with 300 queries: its forward is timed in every run (rank 0)
+    north_star = north_star_forward(torch, msda, dev, tdt, elt, peak) if rank == 0 and not args.no_north_star else None
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -436,6 +439,8 @@ def main():
             "gpu_launches": int(launches * reps), "launches_per_step": launches / chunk,
             "clocks": clk,
         }
+        if north_star:
+            line["north_star_forward"] = north_star
         if extra:
             line["extra"] = extra
         emit(line)
@@ -582,6 +587,52 @@ def run_e2e(torch, msda, sets, w, dev, world, dist, K, elt):
                       f"{ms_copy:.3f} ms/step ({100 * ms_copy / ms:.0f} % of the e2e step); H2D and D2H of all ranks share the host's PCIe / memory path"),
             "path": "pinned host arena -> 1 H2D -> ms_deform_attn_forward + ms_deform_attn_backward (C ABI) -> 1 D2H of out, "
                     "grad_value, grad_loc, grad_attn; 3-slot pipeline on 3 streams; host wall clock"}
+
+
+def north_star_forward(torch, msda, dev, tdt, elt, peak):
+    """Forward at BASELINE.json's target shape -- 4-level COCO 800x1333 pyramid, 300 queries, 8 heads, 4 points -- for the
+    per-GPU batches of configs[4] (N = 2, "C5DEC") and configs[3] (N = 32, "C4DEC"): us per launch, Gsamples/s, fraction of
+    the measured HBM peak by SURVEY 8(d) bytes (`frac`, counts the whole value tensor although 300 queries touch part of it)
+    and by touched bytes (`frac_touched`, rows where a tap lands: the bytes that must move).  Device-resident rotating sets."""
+    from aloception_oss_b200.synthetic import WORKLOADS, device_inputs
+
+    res = {}
+    for name in ("C5DEC", "C4DEC"):
+        w = WORKLOADS[name]
+        fb = w.algorithmic_bytes(elt, False)
+        n_sets = max(2, min(8, int(3 * L2_BYTES / fb) + 2))
+        sets = [device_inputs(w, seed=500 + i, device=dev, dtype=tdt, loc_mode="unit") for i in range(n_sets)]
+        for s_ in sets:
+            s_["out"] = torch.empty((w.N, w.Lq, w.M * w.D), dtype=tdt, device=dev)
+        fn = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], out=s["out"])
+        for i in range(3):
+            fn(sets[i % n_sets])
+        torch.cuda.synchronize()
+        n = 64
+        g = torch.cuda.CUDAGraph()
+        with torch.cuda.graph(g):
+            for i in range(n):
+                fn(sets[i % n_sets])
+        g.replay()
+        torch.cuda.synchronize()
+        times = []
+        for _ in range(7):
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e0.record()
+            g.replay()
+            e1.record()
+            torch.cuda.synchronize()
+            times.append(e0.elapsed_time(e1) / n * 1e3)
+        us = statistics.median(times)
+        tb = touched_bytes(torch, w, sets[0], elt)
+        res[name] = {"workload": workload_string(w, "unit"), "us_per_launch": round(us, 2),
+                     "gsamples_per_s": round(w.samples / us / 1e3, 2), "algorithmic_bytes": fb,
+                     "frac": round(fb / (us * 1e-6) / 1e9 / peak, 4), "touched_bytes": tb["fwd"],
+                     "frac_touched": round(tb["fwd"] / (us * 1e-6) / 1e9 / peak, 4),
+                     "value_rows_touched": tb["value_rows_touched"], "value_rows_total": tb["value_rows_total"]}
+        del g, sets
+        torch.cuda.empty_cache()
+    return res
 
 
 def run_extra(torch, msda, _capi, dev, tdt, elt, peak):
