@@ -82,3 +82,39 @@ def test_sortv_plain_c_program_matches_the_oracle(tmp_path, cuda_device):
     assert "sortv C ABI smoke: OK" in res.stdout
     for v in range(5):
         assert f"variant {v}     ok" in res.stdout, res.stdout
+
+
+# ------------------------------------------------------------------ TensorRT plugin class
+
+PLUGIN_SRC = os.path.join(ROOT, "aloception_oss_b200", "csrc", "trt_plugin", "msda_trt_plugin.cpp")
+PLUGIN_TEST = os.path.join(ROOT, "tests", "c_abi", "trt_plugin_smoke.cpp")
+
+
+def build_plugin_smoke(tmp_path):
+    """The plugin source + its driver, compiled against the MOCK TensorRT header (TensorRT is not in this image)."""
+    from aloception_oss_b200 import _capi
+
+    _capi.build_library()
+    exe = str(tmp_path / "trt_plugin_smoke")
+    pkg = os.path.join(ROOT, "aloception_oss_b200")
+    cmd = ["g++", "-std=c++17", "-O1", "-Wall", "-Wno-comment", "-I" + os.path.join(ROOT, "tests", "c_abi", "mock_tensorrt"),
+           "-I" + os.path.join(ROOT, "include"), "-I" + os.path.join(CUDA, "include"), PLUGIN_SRC, PLUGIN_TEST, "-o", exe,
+           "-L" + pkg, "-lmsda_b200", "-L" + os.path.join(CUDA, "lib64"), "-lcudart",
+           "-Wl,-rpath," + pkg, "-Wl,-rpath," + os.path.join(CUDA, "lib64")]
+    res = subprocess.run(cmd, capture_output=True, text=True)
+    assert res.returncode == 0, res.stderr
+    return exe
+
+
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_trt_plugin_class_compiles_against_the_mock_interface(tmp_path):
+    assert os.path.exists(build_plugin_smoke(tmp_path))
+
+
+@pytest.mark.gpu
+@pytest.mark.skipif(shutil.which("g++") is None, reason="needs g++")
+def test_trt_plugin_class_enqueue_matches_the_operator(tmp_path, cuda_device):
+    exe = build_plugin_smoke(tmp_path)
+    res = subprocess.run([exe], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "TRT plugin smoke: OK" in res.stdout and "enqueue      ok" in res.stdout
