@@ -70,6 +70,15 @@ def main():
             errs = {"out": float((o1 - o2).abs().max() / o2.abs().max())}
             for k, a, b in zip(("grad_value", "grad_loc", "grad_attn"), g1, g2):
                 errs[k] = float((a - b).abs().max() / b.abs().max())
+            # grad_loc away from the floor() discontinuities (tests/_util.near_floor_discontinuity): a sample whose pixel
+            # coordinate is within 2e-5 of an integer may legitimately interpolate either neighbouring pixel pair
+            wh = s0["shapes"].flip(-1).double().view(1, 1, 1, -1, 1, 2)
+            pix = s0["loc"].double() * wh - 0.5
+            near = ((pix - pix.round()).abs() < 2e-5).any(-1)
+            d = (g1[1] - g2[1]).abs().amax(-1)
+            errs["grad_loc_off_discontinuities"] = float(d[~near].max() / g2[1].abs().max())
+            errs["samples_on_discontinuities"] = int(near.sum())
+            errs["samples"] = int(near.numel())
             rec = dict(workload=name, loc=mode, sets=n_sets, max_rel_to_peak_err=errs,
                        ours_fwd_us=round(time_graph(ours_f, sets), 2), ref_fwd_us=round(time_graph(ref_f, sets), 2),
                        ours_bwd_us=round(time_graph(ours_b, sets), 2), ref_bwd_us=round(time_graph(ref_b, sets), 2))
