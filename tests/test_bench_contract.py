@@ -39,3 +39,47 @@ def test_own_arm_fails_loudly_without_a_gpu():
         return
     r = run_bench("--steps", "1", "--warmup", "1", "--no-cpu-baseline", "--no-e2e")
     assert r.returncode != 0 and "no CPU fallback" in (r.stderr + r.stdout)
+
+
+def _load_bench():
+    import importlib.util
+
+    spec = importlib.util.spec_from_file_location("bench_module_under_test", os.path.join(ROOT, "bench.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    return mod
+
+
+def test_both_arms_print_the_same_workload_string():
+    """The driver compares config.workload of the two arms: both come from ONE function."""
+    bench = _load_bench()
+    from aloception_oss_b200.synthetic import WORKLOADS
+
+    s = bench.workload_string(WORKLOADS["C2"], "unit")
+    assert s.startswith("C2: N=2 per GPU") and "Lq=300" in s and "M=8" in s and "P=4" in s and "D=32" in s
+    r = run_bench("--impl", "reference", "--steps", "1", "--warmup", "3")
+    assert json.loads(r.stdout.strip().splitlines()[-1])["config"]["workload"] == s
+
+
+def test_touched_bytes_counts_rows_where_taps_land():
+    """roofline.touched_bytes: value rows are counted only where a bilinear tap lands (distinct (image, pixel, head) rows)."""
+    import torch
+
+    bench = _load_bench()
+    from aloception_oss_b200.synthetic import Workload, level_tensors
+
+    w = Workload("tb", 1, ((4, 4), (2, 2)), 1, M=2, P=1, D=8)
+    shapes, start = level_tensors(w.levels)
+    # head 0: level 0 at pixel centre (1, 1) -> one tap with weight 1 but the 2x2 window is (0..1, 0..1)?  centre of pixel (1,1)
+    # is loc = 1.5/4 -> x = y = 1.0 exactly: floor = 1, taps (1,1), (1,2), (2,1), (2,2) all inside -> 4 rows;
+    # level 1 at loc = -0.3 -> outside the (-1, size) window -> dropped, no rows
+    # head 1: level 0 at loc 0 -> x = -0.5: taps x in {-1, 0}, y in {-1, 0}: only (0, 0) inside -> 1 row; level 1 centre of
+    # pixel (0, 0) = 0.25 -> x = 0: taps (0,0), (0,1), (1,0), (1,1) -> 4 rows
+    loc = torch.tensor([[[[[[0.375, 0.375]], [[-0.3, -0.3]]], [[[0.0, 0.0]], [[0.25, 0.25]]]]]])
+    assert loc.shape == (1, 1, 2, 2, 1, 2)
+    s = {"loc": loc, "shapes": torch.from_numpy(shapes), "start": torch.from_numpy(start)}
+    tb = bench.touched_bytes(torch, w, s, 4)
+    assert tb["value_rows_touched"] == 4 + 0 + 1 + 4 and tb["value_rows_total"] == 1 * 20 * 2
+    nqmlp, nqmd, nsmd = 1 * 1 * 2 * 2 * 1, 1 * 1 * 2 * 8, 1 * 20 * 2 * 8
+    assert tb["fwd"] == 4 * (9 * 8 + 3 * nqmlp + nqmd) + 12 * 2
+    assert tb["bwd"] == 4 * (9 * 8 + nsmd + 6 * nqmlp + nqmd) + 12 * 2

