@@ -16,7 +16,7 @@ import torch.nn.functional as F
 from torch import nn
 from torch.nn.init import constant_, xavier_uniform_
 
-from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, fused_supported,
+from .functions import (MSDeformAttnFunction, MSDeformAttnFusedFunction, deterministic_requested, fused_supported,
                         load_MultiScaleDeformableAttention, ms_deform_attn_core_pytorch)
 
 
@@ -127,7 +127,11 @@ class MSDeformAttn(nn.Module):
             # operator takes ONE storage dtype for value / offsets / logits -- value's -- and does its arithmetic in fp32
             offsets, weights = offsets.to(value.dtype), weights.to(value.dtype)
         # (while a graph is being recorded the unfused op sequence runs: it goes through torch.ops.alonet_custom.*)
+        # (... and when a deterministic backward is requested -- torch.use_deterministic_algorithms / MSDA_DETERMINISTIC --, because
+        # the fused backward accumulates grad_value and the reference-point gradient with fp32 atomics; the plain operator has
+        # the fixed-point mode, MSDA_BWD_DETERMINISTIC)
         if (self.fused and "is_tracing" not in kwargs and not _graph_is_being_recorded()
+                and not (torch.is_grad_enabled() and deterministic_requested())
                 and (reference_points.dtype == value.dtype or reference_points.dtype == torch.float32)
                 and fused_supported(value, input_spatial_shapes, reference_points, offsets, weights)):
             # fp32 reference points stay fp32 next to 16-bit tensors (MSDA_FUSED_REF_F32): a bf16 reference point would be

@@ -132,3 +132,48 @@ def test_deterministic_mode_follows_torch_and_refuses_what_it_does_not_serve(cud
         bwd(x30, deterministic=True)
     with pytest.raises(RuntimeError, match="prezeroed"):
         bwd(x, deterministic=True, prezeroed=msda.begin_backward_zero_fill(x["value"]))
+
+
+def test_module_is_bit_reproducible_under_torch_deterministic_mode(cuda_device):
+    """With torch.use_deterministic_algorithms the mirror module leaves its fused path (whose backward uses fp32 atomics) for
+    the plain operator with the fixed-point backward: parameter and input gradients are identical run to run; without the
+    mode the same module takes the fused kernels."""
+    torch.manual_seed(0)
+    dev = cuda_device
+    mod = msda.MSDeformAttn(256, 4, 8, 4).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    levels = ((20, 27), (10, 14), (5, 7), (3, 4))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    q = torch.randn(2, S, 256, device=dev)
+    src = torch.randn(2, S, 256, device=dev)
+    ref = torch.rand(2, S, 4, 2, device=dev)
+    go = torch.randn(2, S, 256, device=dev)
+
+    def grads():
+        src_ = src.clone().requires_grad_(True)
+        mod.zero_grad(set_to_none=True)
+        out = mod(q, ref, src_, shapes, start)
+        out.backward(go)
+        return [src_.grad.clone()] + [p.grad.clone() for p in mod.parameters()]
+
+    n0 = _capi.kernel_launch_count()
+    base = grads()  # default: fused forward + fused backward (+ zero-fill) = 3 launches
+    assert _capi.kernel_launch_count() == n0 + 3
+    torch.use_deterministic_algorithms(True, warn_only=True)  # (warn_only: cuBLAS needs CUBLAS_WORKSPACE_CONFIG to be strict)
+    try:
+        n0 = _capi.kernel_launch_count()
+        a = grads()
+        assert _capi.kernel_launch_count() == n0 + 5  # forward, absmax, zero-fill, scatter, conversion
+        b = grads()
+    finally:
+        torch.use_deterministic_algorithms(False)
+    # the operator's contribution is bit-reproducible: grad of the module input that feeds `value` goes through value_proj's
+    # GEMM (cuBLAS, deterministic for fixed shapes and no split-K reductions changes) -- compare everything bit for bit
+    for x, y in zip(a, b):
+        assert torch.equal(x, y)
+    for x, y in zip(a, base):
+        assert torch.allclose(x, y, rtol=1e-3, atol=1e-4 * y.abs().max().item())
