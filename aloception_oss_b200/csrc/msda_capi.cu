@@ -674,9 +674,51 @@ int fused_backward_typed(const void* go, const void* value, const int32_t* shape
   return 0;
 }
 
+
+// Large batches: image chunks whose accumulation image stays in L2 between its zero-fill and its scatter.
+// The backward of a call whose grad_value does not fit the 126 MB L2 (C4DEC, N = 32: 728 MB) pays DRAM three times for
+// every touched row -- the fill writes it, the first red fetches it again (evicted meanwhile), the eviction writes it back.
+// Images are independent, so the call is issued as consecutive (zero-fill, scatter[, convert])
+// groups of `nb` images with <= 64 MB of accumulation image each: the reds then land on L2-resident lines and every line
+// goes to DRAM once.  (The reference batches its launches the same way for another reason: im2col_step,
+// ms_deform_attn_cuda.cu:126-150.)  knob "bwd_chunk_mb": 0 = auto (64), -1 = off, else the budget in MB.
+// Measured (profiles/r2_bwd_chunk_and_deterministic.jsonl, C4DEC shapes): N = 8 (182 MB) 77.8 -> 70.7 us, N = 16 (364 MB)
+// 145.7 -> 141.0, N = 32 (728 MB) 282.8 -> 282.5: the groups of a very large call are one-wave, latency-bound launches
+// whose sum equals the whole call, so auto applies the grouping up to 400 MB only.
+std::atomic<int> g_bwd_chunk_mb{0};
+
+template <typename T>
+int backward_chunked(const void* go, const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
+                     const void* attn, void* grad_value, void* gloc, void* gattn, void* workspace, const msda_dims& d,
+                     long long units, cudaStream_t st) {
+  using A = typename msda::AccOf<T>::type;
+  const int knob = g_bwd_chunk_mb.load(std::memory_order_relaxed);
+  const size_t per_image = sizeof(A) * (size_t)d.spatial_size * d.num_heads * d.channels;
+  const size_t budget = (size_t)(knob > 0 ? knob : 64) << 20;
+  const bool whole = knob < 0 || t_prezeroed || d.batch <= 1 || per_image == 0 || per_image * d.batch <= (96u << 20) || units == 0 ||
+                     (knob == 0 && per_image * d.batch > ((size_t)400 << 20));
+  if (whole) return backward_typed<T>(go, value, shapes, start, loc, attn, grad_value, gloc, gattn, workspace, d, units, st);
+  int nb = (int)(budget / per_image);
+  if (nb < 1) nb = 1;
+  const size_t e = sizeof(T);
+  const size_t s_value = (size_t)d.spatial_size * d.num_heads * d.channels, s_out = (size_t)d.num_query * d.num_heads * d.channels,
+               s_attn = (size_t)d.num_query * d.num_heads * d.num_levels * d.num_point;
+  for (int b0 = 0; b0 < d.batch; b0 += nb) {
+    msda_dims c = d;
+    c.batch = d.batch - b0 < nb ? d.batch - b0 : nb;
+    auto at = [&](const void* p, size_t stride, size_t elt) { return p ? (const char*)p + (size_t)b0 * stride * elt : nullptr; };
+    const int rc = backward_typed<T>(at(go, s_out, e), at(value, s_value, e), shapes, start, at(loc, 2 * s_attn, e), at(attn, s_attn, e),
+                                     (void*)at(grad_value, s_value, e), (void*)at(gloc, 2 * s_attn, e), (void*)at(gattn, s_attn, e),
+                                     (void*)at(workspace, s_value, sizeof(A)), c, (long long)c.batch * d.num_query * d.num_heads, st);
+    if (rc) return rc;
+  }
+  return 0;
+}
+
 }  // namespace
 
 extern "C" {
+
 
 int msda_version(void) { return MSDA_ABI_VERSION; }
 
@@ -709,6 +751,7 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "bwd_tile_mode")) return &g_bwd_tile_mode;
   if (!strcmp(name, "bwd_tile_ctas")) return &g_bwd_tile_ctas;
   if (!strcmp(name, "bwd_two_pass")) return &g_bwd_two_pass;
+  if (!strcmp(name, "bwd_chunk_mb")) return &g_bwd_chunk_mb;
   return nullptr;
 }
 
@@ -803,12 +846,12 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
     }
   }
   switch (dtype) {
-    case MSDA_F32: return backward_typed<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_F32: return backward_chunked<float>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
 #ifndef MSDA_DEV_FAST
-    case MSDA_BF16: return backward_typed<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
-    case MSDA_F16: return backward_typed<__half>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_BF16: return backward_chunked<__nv_bfloat16>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_F16: return backward_chunked<__half>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
 #endif
-    case MSDA_F64: return backward_typed<double>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
+    case MSDA_F64: return backward_chunked<double>(grad_output, value, spatial_shapes, level_start_index, sampling_loc, attn_weight, grad_value, grad_sampling_loc, grad_attn_weight, workspace, d, units, st);
   }
   return fail("unreachable");
 }

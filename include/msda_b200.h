@@ -198,6 +198,8 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *                      summed in registers, ONE red per destination and tile; fp32, D = 32, P = 4, L <= 16, S <= 2^19,
  *                      16-byte aligned tensors; other problems keep the unit-ordered kernel)
  *   "bwd_tile_ctas"    0=2, else persistent CTAs per SM of the tile-binned backward (1 or 2)
+ *   "bwd_chunk_mb"     0=auto (64), -1=off, else MB: backward calls whose accumulation image exceeds 96 MB are issued as groups of
+ *                      images of at most this size (zero-fill + scatter per group), so that every grad_value line meets DRAM once
  *   "bwd_two_pass"     0=auto, 1=unit-ordered backward scatters each round right behind its gather, 2=all gather rounds, then
  *                      the fence behind the zero-fill, then all scatter rounds
  */
