@@ -15,12 +15,17 @@
 //     destination's records, reads each record's grad_out row from the tile's shared-memory copy (one LDS.128 per lane, a
 //     whole 128-byte row per quarter warp: conflict-free), accumulates  weight * grad_out  for both pixels in REGISTERS and
 //     forms <grad_out, value row> for both taps (what grad_attn / grad_loc need) in the same pass; it issues ONE red per
-//     (pixel, destination, tile) -- 6-11 x fewer reds than one per tap -- and returns the two dot products to the sample's
-//     owner thread through shared memory;
+//     (pixel, destination, tile) -- 5 x fewer red rows than one per tap on the encoder shape -- and returns the two dot
+//     products to the sample's owner thread through shared memory;
 //   * records whose destination falls outside the window (arbitrary sampling locations: the operator cannot assume
 //     locality) are "destinations of one record": same code, same results, only the privatisation is lost.
 // So BOTH halves of the backward are privatised: the scatter (reds per destination instead of per tap) and the gather
-// (each `value` row of the window is fetched once per tile instead of once per tap: 6-11 x fewer L2->L1 row fills).
+// (each `value` row of the window is fetched once per tile instead of once per tap).
+//
+// MEASURED (profiles/r2_ncu_bwd_tile.md): 5 x fewer red rows and a quarter of the L2 traffic, but the schedule is bound by
+// instruction issue -- 11.4 warp instructions per tap, as many as the unit-ordered kernel spends while IT waits on the red
+// rate -- and ends at 309 us against 265 us on the encoder shape (local +-4 px offsets; random locations 518 vs 292 us).
+// It is therefore an OPT-IN schedule (knob "bwd_tile_mode" = 2), not the default.
 //
 // Results: same maths as msda_bwd_sg_kernel / the reference (ms_deform_im2col_cuda.cuh:87-159); only the order of the
 // fp32 additions differs (tolerances: tests/).  Queries need not be pixel-aligned for correctness -- Lq != sum H*W is
