@@ -22,6 +22,7 @@ F32, BF16, F16, F64 = 0, 1, 2, 3
 BWD_PREZEROED = 1  # MSDA_BWD_PREZEROED
 BWD_DETERMINISTIC = 2  # MSDA_BWD_DETERMINISTIC
 FUSED_REF_F32 = 4  # MSDA_FUSED_REF_F32
+LOC_F32, ATTN_F32 = 0x100, 0x200  # MSDA_LOC_F32 / MSDA_ATTN_F32, OR-ed into the dtype of msda_forward / msda_backward
 
 NVCC_FLAGS = [
     "-O3", "-std=c++17", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo",

@@ -19,6 +19,16 @@
 
 namespace {
 
+// set for the duration of one msda_forward / msda_backward call: MSDA_LOC_F32 / MSDA_ATTN_F32 of its `dtype` argument
+// (fp32 sampling locations / attention weights -- and their gradients -- next to 16-bit value, output and grad_output)
+thread_local int t_io32 = 0;
+struct Io32Scope {
+  explicit Io32Scope(int v) { t_io32 = v; }
+  ~Io32Scope() { t_io32 = 0; }
+};
+size_t loc_elt(size_t e) { return (t_io32 & MSDA_LOC_F32) ? sizeof(float) : e; }
+size_t attn_elt(size_t e) { return (t_io32 & MSDA_ATTN_F32) ? sizeof(float) : e; }
+
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
 std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0};
@@ -198,11 +208,12 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   // except multi-wave decoder calls (C4DEC bf16: 47.5 -> 51.5 us, the clamped taps fetch real rows instead of the zero line).
   const int spk = g_spec_mode.load(std::memory_order_relaxed);
   const bool spec_auto = sizeof(T) == 4 || d.num_query >= 2048 || (long long)d.batch * d.num_query * d.num_heads <= 148LL * 36;
-  const int spec_on = spk == 1 ? 0 : (spk == 2 ? 1 : (spec_auto ? 1 : 0));
+  const int io = sizeof(T) == 4 || FUSED ? 0 : t_io32;
+  const int spec_on = (spk == 1 ? 0 : (spk == 2 ? 1 : (spec_auto ? 1 : 0))) | ((io & MSDA_LOC_F32) ? 2 : 0) | ((io & MSDA_ATTN_F32) ? 4 : 0);
   // TMA-staged coarse levels, persistent CTAs, one per SM (knob "staged_mode")
   const int smk = g_staged_mode.load(std::memory_order_relaxed);
   // (experimental schedules are instantiated for D = 32 only: every shipped model has 32 channels per head)
-  if constexpr (D == 32) if (d.num_levels * d.num_point <= 32 && (smk == 2 || (smk == 0 && staged_mode_auto(d)))) {
+  if constexpr (D == 32) if (io == 0 && d.num_levels * d.num_point <= 32 && (smk == 2 || (smk == 0 && staged_mode_auto(d)))) {
     int warps = g_staged_warps.load(std::memory_order_relaxed);
     if (warps <= 0 || warps > 32) warps = 32;
     const int threads = 32 * warps;
@@ -242,7 +253,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   }
   // patch-ordered persistent kernel for pixel-aligned queries (knob "patch_mode": 0 = auto, 1 = off, 2 = on)
   const int pmk = g_patch_mode.load(std::memory_order_relaxed);
-  if constexpr (D == 32) if (d.num_levels * d.num_point <= 32 && (pmk == 2 || (pmk == 0 && patch_mode_auto(d)))) {  // one sample per lane
+  if constexpr (D == 32) if (io == 0 && d.num_levels * d.num_point <= 32 && (pmk == 2 || (pmk == 0 && patch_mode_auto(d)))) {  // one sample per lane
     int py = g_patch_py.load(std::memory_order_relaxed), px = g_patch_px.load(std::memory_order_relaxed);
     if (py <= 0 || py > MSDA_PATCH_MAX_THREADS / 32) py = 16;
     if (px <= 0) px = 8;
@@ -255,7 +266,7 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
 #define MSDA_FWDP(SR, MINB)                                                                                    \
   e = launch_pdl(msda::msda_fwd_patch_kernel<T, D, MC, FUSED, SR, MINB>, grid, block, SR ? 24 * block.x : 0, st, pdl,  \
                  (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size, \
-                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px, spec_on)
+                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, (const T*)ref, ref_dim, px, spec_on & 1)
     // (a 40-register instantiation for 48 warps per SM spills and measured 139 us vs 113 us on the encoder shape: dropped)
     if (sr2) MSDA_FWDP(true, 2); else MSDA_FWDP(false, 2);
 #undef MSDA_FWDP
@@ -279,17 +290,28 @@ template <typename T>
 int launch_fwd_generic(const void* value, const int32_t* shapes, const int32_t* start, const void* loc,
                        const void* attn, void* out, const msda_dims& d, long long units, cudaStream_t st) {
   const Launch l = unit_launch(units, 8);
-  msda::msda_fwd_generic_kernel<T><<<l.grid, l.block, 0, st>>>(
-      (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,
-      d.channels, d.num_levels, d.num_query, d.num_point, units);
+#define MSDA_FWD_GENERIC(TL, TA)                                                                                    \
+  msda::msda_fwd_generic_kernel<T, TL, TA><<<l.grid, l.block, 0, st>>>(                                              \
+      (const T*)value, shapes, start, (const TL*)loc, (const TA*)attn, (T*)out, d.spatial_size, d.num_heads,         \
+      d.channels, d.num_levels, d.num_query, d.num_point, units)
+  if constexpr (sizeof(T) == 2) {  // mixed precision: fp32 locations / weights next to 16-bit value
+    const bool l32 = (t_io32 & MSDA_LOC_F32) != 0, a32 = (t_io32 & MSDA_ATTN_F32) != 0;
+    if (l32 && a32) MSDA_FWD_GENERIC(float, float);
+    else if (l32) MSDA_FWD_GENERIC(float, T);
+    else if (a32) MSDA_FWD_GENERIC(T, float);
+    else MSDA_FWD_GENERIC(T, T);
+  } else {
+    MSDA_FWD_GENERIC(T, T);
+  }
+#undef MSDA_FWD_GENERIC
   return check_launch("msda_forward(generic)");
 }
 
 template <typename T>
 int forward_typed(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
                   void* out, const msda_dims& d, long long units, cudaStream_t st) {
-  const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(out, 16) && aligned(loc, 2 * sizeof(T)) &&
-                      aligned(attn, sizeof(T));
+  const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(out, 16) && aligned(loc, 2 * loc_elt(sizeof(T))) &&
+                      aligned(attn, attn_elt(sizeof(T)));
   if (vec_ok) {
 #define MSDA_CASE(DD)                                                                                         \
   case DD:                                                                                                    \
@@ -398,7 +420,8 @@ int launch_bwd_vec(const void* go, const void* value, const int32_t* shapes, con
   // knob "bwd_two_pass": 0 = auto, 1 = single pass (scatter of a round right behind its gather), 2 = gather pass / fence / scatter pass
   const int tpk = g_bwd_two_pass.load(std::memory_order_relaxed);
   const bool two_pass = tpk == 2 || (tpk == 0 && bwd_two_pass_auto(d, pdl));
-  const int hm = l.head_major | (two_pass ? 2 : 0);
+  const int io = sizeof(T) == 4 || FUSED ? 0 : t_io32;
+  const int hm = l.head_major | (two_pass ? 2 : 0) | ((io & MSDA_LOC_F32) ? 4 : 0) | ((io & MSDA_ATTN_F32) ? 8 : 0);
   cudaError_t e;
 #define MSDA_BWD(UU)                                                                                          \
   e = cudaLaunchKernelEx(&cfg, msda::msda_bwd_sg_kernel<T, D, MC, UU, FUSED, DET>, go_, value_, shapes, start, loc_, attn_, \
@@ -491,7 +514,13 @@ int backward_deterministic(const void* go, const void* value, const int32_t* sha
     const long long n_go = units * d.channels, n_attn = units * d.num_levels * d.num_point;
     long long blocks = (n_go + 256 * 8 - 1) / (256 * 8);
     if (blocks > 148 * 8) blocks = 148 * 8;
-    msda::msda_absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)go, n_go, (const T*)attn, n_attn, hdr);
+    if (sizeof(T) != 4 && (t_io32 & MSDA_ATTN_F32)) {  // fp32 weights next to 16-bit grad_output: two passes of the same kernel
+      msda::msda_absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)go, n_go, (const T*)nullptr, 0, hdr);
+      if (int rc = check_launch("msda_backward(deterministic: absmax)")) return rc;
+      msda::msda_absmax_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)nullptr, 0, (const float*)attn, n_attn, hdr);
+    } else {
+      msda::msda_absmax_kernel<T><<<(unsigned)blocks, 256, 0, st>>>((const T*)go, n_go, (const T*)attn, n_attn, hdr);
+    }
     if (int rc = check_launch("msda_backward(deterministic: absmax)")) return rc;
   }
   if (int rc = zero_fill(img, n_value * sizeof(long long), st)) return rc;
@@ -550,7 +579,8 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
     }
     if constexpr (!std::is_same<T, double>::value) if (!done) {
       const bool vec_ok = vec_shape_ok(d) && aligned(value, 16) && aligned(go, 16) && aligned(acc, 16) &&
-                          aligned(loc, 2 * sizeof(T)) && aligned(gloc, 2 * sizeof(T)) && aligned(attn, sizeof(T));
+                          aligned(loc, 2 * loc_elt(sizeof(T))) && aligned(gloc, 2 * loc_elt(sizeof(T))) &&
+                          aligned(attn, attn_elt(sizeof(T))) && aligned(gattn, attn_elt(sizeof(T)));
       if (vec_ok) {
         int rc = -1;
 #define MSDA_CASE(DD)                                                                                         \
@@ -575,9 +605,20 @@ int backward_typed(const void* go, const void* value, const int32_t* shapes, con
     }
     if (!done) {
       const Launch l = unit_launch(units, 8);
-      msda::msda_bwd_generic_kernel<T><<<l.grid, l.block, 0, st>>>(
-          (const T*)go, (const T*)value, shapes, start, (const T*)loc, (const T*)attn, acc, (T*)gloc, (T*)gattn,
-          d.spatial_size, d.num_heads, d.channels, d.num_levels, d.num_query, d.num_point, units);
+#define MSDA_BWD_GENERIC(TL, TA)                                                                                          \
+  msda::msda_bwd_generic_kernel<T, TL, TA><<<l.grid, l.block, 0, st>>>(                                                    \
+      (const T*)go, (const T*)value, shapes, start, (const TL*)loc, (const TA*)attn, acc, (TL*)gloc, (TA*)gattn,           \
+      d.spatial_size, d.num_heads, d.channels, d.num_levels, d.num_query, d.num_point, units)
+      if constexpr (sizeof(T) == 2) {  // mixed precision: fp32 locations / weights (and their gradients) next to 16-bit value
+        const bool l32 = (t_io32 & MSDA_LOC_F32) != 0, a32 = (t_io32 & MSDA_ATTN_F32) != 0;
+        if (l32 && a32) MSDA_BWD_GENERIC(float, float);
+        else if (l32) MSDA_BWD_GENERIC(float, T);
+        else if (a32) MSDA_BWD_GENERIC(T, float);
+        else MSDA_BWD_GENERIC(T, T);
+      } else {
+        MSDA_BWD_GENERIC(T, T);
+      }
+#undef MSDA_BWD_GENERIC
       if (int rc = check_launch("msda_backward(generic)")) return rc;
     }
   }
@@ -707,8 +748,9 @@ int backward_chunked(const void* go, const void* value, const int32_t* shapes, c
     msda_dims c = d;
     c.batch = d.batch - b0 < nb ? d.batch - b0 : nb;
     auto at = [&](const void* p, size_t stride, size_t elt) { return p ? (const char*)p + (size_t)b0 * stride * elt : nullptr; };
-    const int rc = backward_typed<T>(at(go, s_out, e), at(value, s_value, e), shapes, start, at(loc, 2 * s_attn, e), at(attn, s_attn, e),
-                                     (void*)at(grad_value, s_value, e), (void*)at(gloc, 2 * s_attn, e), (void*)at(gattn, s_attn, e),
+    const int rc = backward_typed<T>(at(go, s_out, e), at(value, s_value, e), shapes, start, at(loc, 2 * s_attn, loc_elt(e)),
+                                     at(attn, s_attn, attn_elt(e)), (void*)at(grad_value, s_value, e),
+                                     (void*)at(gloc, 2 * s_attn, loc_elt(e)), (void*)at(gattn, s_attn, attn_elt(e)),
                                      (void*)at(workspace, s_value, sizeof(A)), c, (long long)c.batch * d.num_query * d.num_heads, st);
     if (rc) return rc;
   }
@@ -773,7 +815,11 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
                  const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims, int dtype,
                  void* stream) {
   g_err[0] = 0;
+  const int io = dtype & (MSDA_LOC_F32 | MSDA_ATTN_F32);
+  dtype &= ~(MSDA_LOC_F32 | MSDA_ATTN_F32);
   if (int rc = validate_dims(dims, dtype)) return rc;
+  if (io && dtype == MSDA_F64) return fail("MSDA_LOC_F32 / MSDA_ATTN_F32 make no sense for MSDA_F64");
+  Io32Scope io_scope(dtype == MSDA_F32 ? 0 : io);
   const msda_dims& d = *dims;
   const long long units = (long long)d.batch * d.num_query * d.num_heads;
   if (units == 0 || d.channels == 0) return 0;  // empty output
@@ -796,6 +842,7 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
 
 size_t msda_backward_workspace_bytes_ex(const msda_dims* dims, int dtype, int flags) {
   if (!dims) return 0;
+  dtype &= ~(MSDA_LOC_F32 | MSDA_ATTN_F32);
   const size_t n_value = (size_t)dims->batch * dims->spatial_size * dims->num_heads * dims->channels;
   if (flags & MSDA_BWD_DETERMINISTIC) return n_value ? kDetHeader + sizeof(long long) * n_value : 0;
   if (dtype == MSDA_BF16 || dtype == MSDA_F16) return sizeof(float) * n_value;
@@ -809,7 +856,11 @@ int msda_backward(const void* grad_output, const void* value, const int32_t* spa
                   void* grad_value, void* grad_sampling_loc, void* grad_attn_weight, void* workspace,
                   size_t workspace_bytes, const msda_dims* dims, int dtype, int flags, void* stream) {
   g_err[0] = 0;
+  const int io = dtype & (MSDA_LOC_F32 | MSDA_ATTN_F32);
+  dtype &= ~(MSDA_LOC_F32 | MSDA_ATTN_F32);
   if (int rc = validate_dims(dims, dtype)) return rc;
+  if (io && dtype == MSDA_F64) return fail("MSDA_LOC_F32 / MSDA_ATTN_F32 make no sense for MSDA_F64");
+  Io32Scope io_scope(dtype == MSDA_F32 ? 0 : io);
   if (flags & ~(MSDA_BWD_PREZEROED | MSDA_BWD_DETERMINISTIC)) return fail("unknown flags 0x%x", flags);
   const bool det = (flags & MSDA_BWD_DETERMINISTIC) != 0;
   if (det && (flags & MSDA_BWD_PREZEROED)) return fail("MSDA_BWD_DETERMINISTIC cannot be combined with MSDA_BWD_PREZEROED");

@@ -332,16 +332,24 @@ struct SampleParams {
   int H, W, st;     // level shape and first row
 };
 
-// plain operator: locations and (already normalised) weights are inputs
+// plain operator: locations and (already normalised) weights are inputs.  l32 / a32: the tensor is fp32 although T is a 16-bit
+// type (mixed precision, MSDA_LOC_F32 / MSDA_ATTN_F32: torch.autocast leaves the location arithmetic in fp32 -- a bf16 location
+// is quantised to 1/256 of the image); the caller then passes unit pointers whose BYTE offset is that of the fp32 tensor
+// (unit_ptr below), and they are re-read as float here.
 template <typename T>
 __device__ __forceinline__ SampleParams load_params(const T* __restrict__ u_loc, const T* __restrict__ u_att,
                                                     const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
-                                                    int s, bool have, float inv_p) {
+                                                    int s, bool have, float inv_p, bool l32 = false, bool a32 = false) {
   SampleParams p;
   const int si = have ? s : 0;
   const int l = have ? level_of(si, inv_p) : 0;
-  load_xy(u_loc + 2 * si, p.lx, p.ly);
-  p.a = load_s(u_att + si);
+  if (sizeof(T) != 4 && l32) {
+    const float2 t = __ldg(reinterpret_cast<const float2*>(u_loc) + si);
+    p.lx = t.x; p.ly = t.y;
+  } else {
+    load_xy(u_loc + 2 * si, p.lx, p.ly);
+  }
+  p.a = (sizeof(T) != 4 && a32) ? __ldg(reinterpret_cast<const float*>(u_att) + si) : load_s(u_att + si);
   p.H = __ldg(shapes + 2 * l);
   p.W = __ldg(shapes + 2 * l + 1);
   p.st = __ldg(start + l);
@@ -719,8 +727,10 @@ msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
   const int cl = lane % LPR;
   const int LP = L * P;
   const long long u = (long long)b * QM + uq;
-  const T* __restrict__ u_loc = loc + u * (LP * 2);
-  const T* __restrict__ u_att = attn + u * LP;
+  const bool l32 = sizeof(T) != 4 && !FUSED && (spec_on & 2) != 0;  // bits 1 / 2 of the word: fp32 locations / weights next to
+  const bool a32 = sizeof(T) != 4 && !FUSED && (spec_on & 4) != 0;  // 16-bit value (load_params); element offsets double
+  const T* __restrict__ u_loc = loc + u * (LP * 2) * (l32 ? 2 : 1);
+  const T* __restrict__ u_att = attn + u * LP * (a32 ? 2 : 1);
   const T* __restrict__ vb = value + (long long)b * S * MD + (m * D + cl * VEC);
 
   constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
@@ -728,7 +738,7 @@ msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
   float o[N_OUT];
   int first;
   bool owner;
-  bool spec = spec_on != 0;  // try the speculative regular-window gather first (see msda_fwd_gather_pass)
+  bool spec = (spec_on & 1) != 0;  // try the speculative regular-window gather first (see msda_fwd_gather_pass)
   for (;;) {
 #pragma unroll
     for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
@@ -741,7 +751,7 @@ msda_fwd_unit(const T* __restrict__ value, const int32_t* __restrict__ shapes,
         float odx, ody;
         sp = fused_params<T>(u_loc, u_att, ref, ((long long)b * (QM / M) + uq / M) * (L * RD), RD, r32, shapes, start, lane, have, inv_p, P, l, odx, ody);
       } else {
-        sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+        sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, l32, a32);
       }
       // the regular window needs levels of at least 2 x 2 pixels (warp-uniform; the decision sticks for the unit)
       if (spec && !__all_sync(0xffffffffu, !have || (sp.H >= 2 && sp.W >= 2))) {
@@ -1211,13 +1221,15 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
   const int MD = M * D;
   const int lane = threadIdx.x & 31;
   const bool two_pass = (head_major & 2) != 0;  // bit 1 of the scheduling word: gather pass, fence, scatter pass
+  const bool l32 = sizeof(T) != 4 && !FUSED && (head_major & 4) != 0;  // bits 2 / 3: fp32 locations / weights (and their gradients)
+  const bool a32 = sizeof(T) != 4 && !FUSED && (head_major & 8) != 0;  // next to 16-bit value (mixed precision, see load_params)
   int uq, m;
   if (!unit_of_warp(M, QM, head_major & 1, uq, m)) return;  // warp-uniform (an exited warp needs no fence)
   const int g = lane / LPR, cl = lane % LPR;
   const int LP = L * P;
   const long long u = (long long)blockIdx.y * QM + uq;
-  const T* __restrict__ u_loc = loc + u * (LP * 2);
-  const T* __restrict__ u_att = attn + u * LP;
+  const T* __restrict__ u_loc = loc + u * (LP * 2) * (l32 ? 2 : 1);
+  const T* __restrict__ u_att = attn + u * LP * (a32 ? 2 : 1);
   const long long voff = (long long)blockIdx.y * S * MD + (m * D + cl * VEC);
   const T* __restrict__ vb = value + voff;
   float* __restrict__ gb = gv + voff;
@@ -1242,7 +1254,7 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
     if constexpr (FUSED) {
       sp = fused_params<T>(u_loc, u_att, ref, ((long long)blockIdx.y * (QM / M) + uq / M) * (L * RD), RD, r32, shapes, start, lane, have, inv_p, P, lvl, odx, ody);
     } else {
-      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p);
+      sp = load_params<T>(u_loc, u_att, shapes, start, base + lane, have, inv_p, l32, a32);
     }
     finish_geometry(sp, have, MD, sg, ge);
     const float a = (FUSED || ge.inside) ? sp.a : 0.f;  // outside sample: every gradient is exactly zero (FUSED keeps the softmax weight)
@@ -1357,8 +1369,10 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
       const long long sidx = u * LP + base + lane;
       if constexpr (!FUSED) {
         if (have) {  // coalesced: 32 consecutive samples of the unit
-          gattn[sidx] = from_acc<T>(g_a);
-          store_xy(gloc + 2 * sidx, g_lx, g_ly);
+          if (a32) reinterpret_cast<float*>(gattn)[sidx] = g_a;
+          else gattn[sidx] = from_acc<T>(g_a);
+          if (l32) store_xy(reinterpret_cast<float*>(gloc) + 2 * sidx, g_lx, g_ly);
+          else store_xy(gloc + 2 * sidx, g_lx, g_ly);
         }
       } else {
         // softmax backward over the unit's samples:  g_logit_i = A_i * (g_A_i - sum_j A_j g_A_j)
@@ -1421,12 +1435,13 @@ msda_bwd_sg_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
 
 // ------------------------------------------------------------------------------------------------
 // GENERIC kernels: any D, L, P; T in {float, double, bf16, half}.  Warp per unit, lanes over channels.
+// TL / TA: storage type of sampling_loc / attn_weight and of their gradients (float next to a 16-bit T: mixed precision).
 // ------------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, typename TL = T, typename TA = T>
 __global__ void __launch_bounds__(256)
 msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes,
-                        const int32_t* __restrict__ start, const T* __restrict__ loc,
-                        const T* __restrict__ attn, T* __restrict__ out,
+                        const int32_t* __restrict__ start, const TL* __restrict__ loc,
+                        const TA* __restrict__ attn, T* __restrict__ out,
                         int S, int M, int D, int L, int Lq, int P, long long units) {
   using A = typename AccOf<T>::type;
   const int lane = threadIdx.x & 31;
@@ -1436,8 +1451,8 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__
   const long long b = (u / M) / Lq;
   const int LP = L * P;
   const long long MD = (long long)M * D;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
-  const T* __restrict__ u_att = attn + u * LP;
+  const TL* __restrict__ u_loc = loc + u * LP * 2;
+  const TA* __restrict__ u_att = attn + u * LP;
   const T* __restrict__ vb = value + b * (long long)S * MD + (long long)m * D;
 
   for (int c0 = 0; c0 < D; c0 += 32) {
@@ -1464,12 +1479,12 @@ msda_fwd_generic_kernel(const T* __restrict__ value, const int32_t* __restrict__
   }
 }
 
-template <typename T>
+template <typename T, typename TL = T, typename TA = T>
 __global__ void __launch_bounds__(256)
 msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ value,
                         const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
-                        const T* __restrict__ loc, const T* __restrict__ attn,
-                        typename AccOf<T>::type* __restrict__ gv, T* __restrict__ gloc, T* __restrict__ gattn,
+                        const TL* __restrict__ loc, const TA* __restrict__ attn,
+                        typename AccOf<T>::type* __restrict__ gv, TL* __restrict__ gloc, TA* __restrict__ gattn,
                         int S, int M, int D, int L, int Lq, int P, long long units) {
   using A = typename AccOf<T>::type;
   const int lane = threadIdx.x & 31;
@@ -1479,8 +1494,8 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
   const long long b = (u / M) / Lq;
   const int LP = L * P;
   const long long MD = (long long)M * D;
-  const T* __restrict__ u_loc = loc + u * LP * 2;
-  const T* __restrict__ u_att = attn + u * LP;
+  const TL* __restrict__ u_loc = loc + u * LP * 2;
+  const TA* __restrict__ u_att = attn + u * LP;
   const T* __restrict__ u_go = grad_out + u * D;
   const long long voff = b * (long long)S * MD + (long long)m * D;
 
@@ -1518,9 +1533,9 @@ msda_bwd_generic_kernel(const T* __restrict__ grad_out, const T* __restrict__ va
       }
       if (lane == 0) {
         const long long sidx = u * LP + s;
-        gattn[sidx] = from_acc<T>(s_a);
-        gloc[2 * sidx] = from_acc<T>((A)W * a * s_x);
-        gloc[2 * sidx + 1] = from_acc<T>((A)H * a * s_y);
+        gattn[sidx] = from_acc<TA>(s_a);
+        gloc[2 * sidx] = from_acc<TL>((A)W * a * s_x);
+        gloc[2 * sidx + 1] = from_acc<TL>((A)H * a * s_y);
       }
     }
   }

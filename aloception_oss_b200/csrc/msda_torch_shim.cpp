@@ -50,8 +50,12 @@ msda_dims check_inputs(const at::Tensor& value, const at::Tensor& shapes, const 
   TORCH_CHECK(loc.is_cuda(), "sampling_loc must be a CUDA tensor");
   TORCH_CHECK(attn.is_cuda(), "attn_weight must be a CUDA tensor");
   if (grad_output) TORCH_CHECK(grad_output->is_cuda(), "grad_output must be a CUDA tensor");
-  TORCH_CHECK(loc.scalar_type() == value.scalar_type(), "sampling_loc has dtype ", loc.scalar_type(), ", expected ", value.scalar_type(), " (same as value)");
-  TORCH_CHECK(attn.scalar_type() == value.scalar_type(), "attn_weight has dtype ", attn.scalar_type(), ", expected ", value.scalar_type(), " (same as value)");
+  // mixed precision: sampling_loc / attn_weight may stay float32 next to 16-bit value (MSDA_LOC_F32 / MSDA_ATTN_F32)
+  const bool half = value.scalar_type() == at::kBFloat16 || value.scalar_type() == at::kHalf;
+  TORCH_CHECK(loc.scalar_type() == value.scalar_type() || (half && loc.scalar_type() == at::kFloat), "sampling_loc has dtype ",
+              loc.scalar_type(), ", expected ", value.scalar_type(), " (same as value)");
+  TORCH_CHECK(attn.scalar_type() == value.scalar_type() || (half && attn.scalar_type() == at::kFloat), "attn_weight has dtype ",
+              attn.scalar_type(), ", expected ", value.scalar_type(), " (same as value)");
   TORCH_CHECK(loc.device() == value.device() && attn.device() == value.device(), "sampling_loc / attn_weight are not on value's device");
   TORCH_CHECK(value.dim() == 4, "value must be (N, S, M, D), got ", value.sizes());
   TORCH_CHECK(loc.dim() == 6 && loc.size(5) == 2, "sampling_loc must be (N, Lq, M, L, P, 2), got ", loc.sizes());
@@ -79,6 +83,14 @@ msda_dims check_inputs(const at::Tensor& value, const at::Tensor& shapes, const 
 
 const void* ptr(const at::Tensor& t) { return t.numel() ? t.data_ptr() : nullptr; }
 
+// the C ABI's dtype word: value's type plus the mixed-precision bits
+int io_dtype(const at::Tensor& value, const at::Tensor& loc, const at::Tensor& attn) {
+  int dt = dtype_of(value);
+  if (loc.scalar_type() != value.scalar_type()) dt |= MSDA_LOC_F32;
+  if (attn.scalar_type() != value.scalar_type()) dt |= MSDA_ATTN_F32;
+  return dt;
+}
+
 at::Tensor forward_cuda(const at::Tensor& value, const at::Tensor& spatial_shapes, const at::Tensor& level_start_index,
                         const at::Tensor& sampling_loc, const at::Tensor& attn_weight, int64_t im2col_step) {
   const msda_dims d = check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, nullptr);
@@ -86,7 +98,8 @@ at::Tensor forward_cuda(const at::Tensor& value, const at::Tensor& spatial_shape
   const c10::cuda::CUDAGuard guard(value.device());
   at::Tensor out = at::empty({d.batch, d.num_query, (int64_t)d.num_heads * d.channels}, value.options());
   const int rc = msda_forward(ptr(value), (const int32_t*)ptr(shapes), (const int32_t*)ptr(start), ptr(sampling_loc), ptr(attn_weight),
-                              const_cast<void*>(ptr(out)), &d, dtype_of(value), (void*)at::cuda::getCurrentCUDAStream().stream());
+                              const_cast<void*>(ptr(out)), &d, io_dtype(value, sampling_loc, attn_weight),
+                              (void*)at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, "msda_forward failed: ", msda_last_error_string());
   return out;
 }
@@ -102,7 +115,7 @@ std::vector<at::Tensor> backward_cuda(const at::Tensor& value, const at::Tensor&
   const msda_dims d = check_inputs(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, im2col_step, &grad_output);
   const at::Tensor shapes = meta_i32(spatial_shapes, "spatial_shapes"), start = meta_i32(level_start_index, "level_start_index");
   const c10::cuda::CUDAGuard guard(value.device());
-  const int dt = dtype_of(value);
+  const int dt = io_dtype(value, sampling_loc, attn_weight);
   int flags = 0;
   // an implicit request (torch.use_deterministic_algorithms / MSDA_DETERMINISTIC) applies where the mode is served
   if (deterministic_requested() && dt != MSDA_F64 && (d.channels == 16 || d.channels == 32 || d.channels == 64 || d.channels == 128))

@@ -85,8 +85,10 @@ def _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_
                    ("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra])
     if value.dtype not in _DTYPES:
         raise RuntimeError(f"ms_deform_attn: unsupported dtype {value.dtype} (float32, float64, bfloat16, float16)")
+    half = value.dtype in (torch.bfloat16, torch.float16)
     for name, t in (("sampling_loc", sampling_loc), ("attn_weight", attn_weight), *extra):
-        if t.dtype != value.dtype:
+        # mixed precision: sampling_loc / attn_weight may stay float32 next to 16-bit value (MSDA_LOC_F32 / MSDA_ATTN_F32)
+        if t.dtype != value.dtype and not (half and t.dtype == torch.float32 and name != "grad_output"):
             raise RuntimeError(f"{name} has dtype {t.dtype}, expected {value.dtype} (same as value)")
         if t.device != value.device:
             raise RuntimeError(f"{name} is on {t.device}, value on {value.device}")
@@ -99,6 +101,16 @@ def _common_checks(value, spatial_shapes, level_start_index, sampling_loc, attn_
     if batch > 0 and (step <= 0 or batch % step != 0):
         raise RuntimeError(f"batch({batch}) must divide im2col_step({step})")
     return dims
+
+
+def _io_dtype(value, sampling_loc, attn_weight):
+    """The C ABI's dtype word: value's type, plus MSDA_LOC_F32 / MSDA_ATTN_F32 for fp32 locations / weights next to 16-bit value."""
+    dt = _DTYPES[value.dtype]
+    if sampling_loc.dtype != value.dtype:
+        dt |= _capi.LOC_F32
+    if attn_weight.dtype != value.dtype:
+        dt |= _capi.ATTN_F32
+    return dt
 
 
 def _ptr(t):
@@ -160,7 +172,7 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     out = torch.empty(oshape, dtype=value.dtype, device=value.device) if out is None else _check_out(out, oshape, value, "out")
     with _on_device(value) as stream:
         rc = _capi.lib().msda_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight),
-                                      _ptr(out), ctypes.byref(dims), _DTYPES[value.dtype], stream)
+                                      _ptr(out), ctypes.byref(dims), _io_dtype(value, sampling_loc, attn_weight), stream)
     if rc != 0:
         raise RuntimeError("msda_forward failed: " + _capi.last_error())
     return out
@@ -234,7 +246,7 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
     shapes = _meta_i32(spatial_shapes, "spatial_shapes")
     start = _meta_i32(level_start_index, "level_start_index")
     L = _capi.lib()
-    dt = _DTYPES[value.dtype]
+    dt = _io_dtype(value, sampling_loc, attn_weight)
     det = deterministic_requested() if deterministic is None else bool(deterministic)
     if det and deterministic is None and (value.dtype == torch.float64 or dims.channels not in (16, 32, 64, 128)):
         det = False  # (an implicit request must not break float64 gradcheck / odd channel counts: they keep the reds)
@@ -263,8 +275,8 @@ def ms_deform_attn_backward(value, spatial_shapes, level_start_index, sampling_l
         if pre_gv is not None:
             raise RuntimeError("grads= and prezeroed= both name a grad_value buffer")
         grad_value = _check_out(grads[0], value.shape, value, "grads[0]")
-        grad_loc = _check_out(grads[1], sampling_loc.shape, value, "grads[1]")
-        grad_attn = _check_out(grads[2], attn_weight.shape, value, "grads[2]")
+        grad_loc = _check_out(grads[1], sampling_loc.shape, sampling_loc, "grads[1]")
+        grad_attn = _check_out(grads[2], attn_weight.shape, attn_weight, "grads[2]")
     if ws is None and ws_bytes:
         ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device)
     with _on_device(value) as stream:

@@ -141,8 +141,8 @@ class MSDeformAttn(nn.Module):
                                                      weights.contiguous())
             return self.output_proj(output)
         if reference_points.dtype != value.dtype and "is_tracing" not in kwargs:
-            # unfused path: the location arithmetic below runs in fp32 (type promotion with the fp32 points); the operator then
-            # stores the locations in value's dtype -- prefer the fused path for 16-bit training
+            # unfused path: the location arithmetic below runs in fp32 (type promotion with the fp32 points) and the operator
+            # takes the fp32 locations as they are next to 16-bit value (MSDA_LOC_F32)
             offsets = offsets.to(reference_points.dtype)
         weights = F.softmax(weights, -1).view(N, Len_q, self.n_heads, self.n_levels, self.n_points)
         if reference_points.shape[-1] == 2:
@@ -157,7 +157,11 @@ class MSDeformAttn(nn.Module):
         if "is_tracing" in kwargs:
             output = ms_deform_attn_core_pytorch(value, input_spatial_shapes, locations, weights)
         else:
+            half = value.dtype in (torch.bfloat16, torch.float16)
+            if not (half and locations.dtype == torch.float32):
+                locations = locations.to(value.dtype)
+            if not (half and weights.dtype == torch.float32):
+                weights = weights.to(value.dtype)
             output = MSDeformAttnFunction.apply(value.contiguous(), input_spatial_shapes, input_level_start_index,
-                                                locations.to(value.dtype).contiguous(), weights.to(value.dtype).contiguous(),
-                                                self.im2col_step)
+                                                locations.contiguous(), weights.contiguous(), self.im2col_step)
         return self.output_proj(output)

@@ -39,6 +39,13 @@ extern "C" {
  * The reference op dispatches float and double only (AT_DISPATCH_FLOATING_TYPES,
  * ms_deform_attn_cuda.cu:64,134); bf16 / f16 storage with fp32 arithmetic is an extension. */
 enum msda_dtype { MSDA_F32 = 0, MSDA_BF16 = 1, MSDA_F16 = 2, MSDA_F64 = 3 };
+/* Mixed precision (msda_forward / msda_backward, OR-ed into `dtype` next to MSDA_BF16 / MSDA_F16): sampling_loc (and
+ * grad_sampling_loc) / attn_weight (and grad_attn_weight) are fp32 while value, output and grad_output are 16-bit.  This is
+ * what torch.autocast hands the operator -- the Linear layers emit bf16, the location arithmetic with the fp32 reference
+ * points stays fp32 -- and it matters: a bf16 location is quantised to 1/256 of the image (0.65 px on a 167-px level).
+ * Every kernel family serves it (the deterministic backward too); ignored for MSDA_F32, an error for MSDA_F64. */
+#define MSDA_LOC_F32 0x100
+#define MSDA_ATTN_F32 0x200
 
 /* Problem sizes, in the reference's naming (ms_deform_attn_cuda.cu:40-48). */
 typedef struct msda_dims {

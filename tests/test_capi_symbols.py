@@ -111,6 +111,16 @@ def test_prezeroed_flag_and_zero_fill_validation():
     # workspace of the deterministic mode: 256-byte header + an int64 image of grad_value
     assert lib.msda_backward_workspace_bytes_ex(ctypes.byref(dims), _capi.F32, _capi.BWD_DETERMINISTIC) == 256 + 8 * 4 * 32
     assert lib.msda_backward_workspace_bytes_ex(ctypes.byref(dims), _capi.BF16, 0) == lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.BF16)
+    # mixed-precision bits of the dtype word (MSDA_LOC_F32 / MSDA_ATTN_F32): same workspace as the plain 16-bit call, valid next
+    # to MSDA_BF16 / MSDA_F16 (and ignored next to MSDA_F32), an error next to MSDA_F64
+    mixed = _capi.BF16 | _capi.LOC_F32 | _capi.ATTN_F32
+    assert lib.msda_backward_workspace_bytes_ex(ctypes.byref(dims), mixed, 0) == lib.msda_backward_workspace_bytes(ctypes.byref(dims), _capi.BF16)
+    rc = lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), _capi.F64 | _capi.LOC_F32, None)
+    assert rc != 0 and "make no sense for MSDA_F64" in _capi.last_error()
+    rc = lib.msda_forward(None, None, None, None, None, None, ctypes.byref(dims), 0x400, None)
+    assert rc != 0 and "dtype" in _capi.last_error()
+    hdr = open(_capi.HEADER).read()
+    assert "#define MSDA_LOC_F32 0x%x" % _capi.LOC_F32 in hdr and "#define MSDA_ATTN_F32 0x%x" % _capi.ATTN_F32 in hdr
     # the flag itself passes flag validation (the call then fails on the NULL tensors, not on the flag)
     rc = lib.msda_backward(None, None, None, None, None, None, None, None, None, None, 0, ctypes.byref(dims), _capi.F32,
                            _capi.BWD_PREZEROED, None)

@@ -190,3 +190,45 @@ def test_module_under_autocast_tracks_the_fp32_module(cuda_device):
     scale = want.pow(2).mean().sqrt().item()
     assert e_new < 3e-2 * scale, (e_new, scale)
     assert e_new < e_old, (e_new, e_old)
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+def test_unfused_module_under_autocast_keeps_fp32_locations(dtype, cuda_device):
+    """fused=False reproduces the reference's op sequence; under autocast the plain operator then gets 16-bit value next to
+    fp32 sampling locations / weights (MSDA_LOC_F32 | MSDA_ATTN_F32) and must track the fp32 module as well as the fused path
+    does (both read the exact locations)."""
+    msda.load_ops()
+    dev = cuda_device
+    torch.manual_seed(0)
+    mod = msda.MSDeformAttn(256, 4, 8, 4, fused=False).to(dev)
+    with torch.no_grad():
+        mod.sampling_offsets.weight.normal_(0, 0.02)
+        mod.attention_weights.weight.normal_(0, 0.1)
+    fused = msda.MSDeformAttn(256, 4, 8, 4, fused=True).to(dev)
+    fused.load_state_dict(mod.state_dict())
+    levels = ((100, 167), (50, 84), (25, 42), (13, 21))
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    q, src, ref = torch.randn(2, 300, 256, device=dev), torch.randn(2, S, 256, device=dev), torch.rand(2, 300, 4, 2, device=dev)
+
+    def run(m, cast):
+        m.zero_grad()
+        qq = q.clone().requires_grad_(True)
+        if cast:
+            with torch.autocast("cuda", dtype=dtype):
+                out = m(qq, ref, src, shapes, start)
+        else:
+            out = m(qq, ref, src, shapes, start)
+        out.float().square().sum().backward()
+        return out.detach().float(), qq.grad, m.sampling_offsets.weight.grad.clone()
+
+    want, got, fus = run(mod, False), run(mod, True), run(fused, True)
+    for name, g, f, w in zip(("out", "grad_query", "grad_W_offsets"), got, fus, want):
+        scale = w.pow(2).mean().sqrt().item()
+        e_g = (g.float() - w).pow(2).mean().sqrt().item()
+        e_f = (f.float() - w).pow(2).mean().sqrt().item()
+        # (gradients through the piecewise-constant bilinear derivative: see tests/test_ref_module_autocast_gpu.py)
+        assert e_g < (5e-2 if name == "out" else 4e-1) * scale, (name, e_g, scale)
+        assert e_g < 2.0 * e_f + 1e-3 * scale, (name, e_g, e_f)

@@ -126,6 +126,84 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
     assert_close(got[3], want[3], 1e-2, 1e-2 * rms(want[3]), "grad_attn")
 
 
+@pytest.mark.parametrize("which", ["loc", "attn", "both"])
+@pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
+@pytest.mark.parametrize("w", SHAPES[:6], ids=lambda w: w.name)
+def test_mixed_precision_fp32_locations_and_weights(w, dtype, which, cuda_device):
+    """MSDA_LOC_F32 / MSDA_ATTN_F32: what torch.autocast hands the operator -- 16-bit value / grad_output, fp32 sampling_loc
+    and / or attn_weight.  The fp32 tensors are read unrounded (oracle on value / grad_out rounded, loc / attn exact) and
+    their gradients come back in fp32."""
+    x = torch_inputs(w, seed=16, loc_mode="wide")
+    keep = {"loc": ("loc",), "attn": ("attn",), "both": ("loc", "attn")}[which]
+    xr = {k: (v.to(dtype).float() if v.is_floating_point() and k not in keep else v) for k, v in x.items()}
+    dev = cuda_device
+    value, go = xr["value"].to(dtype).to(dev).requires_grad_(True), xr["grad_out"].to(dtype).to(dev)
+    loc = (xr["loc"] if "loc" in keep else xr["loc"].to(dtype)).to(dev).requires_grad_(True)
+    attn = (xr["attn"] if "attn" in keep else xr["attn"].to(dtype)).to(dev).requires_grad_(True)
+    out = msda.MSDeformAttnFunction.apply(value, xr["shapes"].to(dev), xr["start"].to(dev), loc, attn, 64)
+    out.backward(go)
+    assert out.dtype == dtype and value.grad.dtype == dtype
+    assert loc.grad.dtype == loc.dtype and attn.grad.dtype == attn.dtype
+    want = oracle64(xr)
+    got = [t.detach().double().cpu().numpy() for t in (out, value.grad, loc.grad, attn.grad)]
+    assert_close(got[0], want[0], 1e-2, 1e-2 * rms(want[0]), "out")
+    assert_close(got[1], want[1], 1e-2, 1e-2 * rms(want[1]), "grad_value")
+    # the fp32 gradients are not rounded to 16 bits: only value / grad_output's rounding (already in `want`) and fp32 sums remain
+    if "loc" in keep:
+        assert_close_grad_loc(got[2], want[2], xr["loc"].numpy(), xr["shapes"].numpy(), 1e-4)
+    else:
+        assert_close(got[2], want[2], 1e-2, 1e-2 * rms(want[2]), "grad_loc")
+    assert_close_grad(got[3], want[3], 1e-4 if "attn" in keep else 1e-2, "grad_attn")
+    # forward only, through the functional entry and the registered op
+    with torch.no_grad():
+        o2 = msda.ms_deform_attn_forward(value, xr["shapes"].to(dev), xr["start"].to(dev), loc, attn)
+        o3 = torch.ops.alonet_custom.ms_deform_attn_forward(value, xr["shapes"].to(dev), xr["start"].to(dev), loc, attn, 64)
+    assert torch.equal(o2, out) and torch.equal(o3, out)
+
+
+@pytest.mark.parametrize("det", [False, True], ids=["reds", "deterministic"])
+def test_mixed_precision_full_size_call_and_buffers(det, cuda_device):
+    """An encoder-sized mixed-precision call (bf16 value, fp32 loc / attn) against the all-fp32 operator on the same rounded
+    value / grad_output: same function up to bf16 rounding of out / grad_value; caller-provided fp32 gradient buffers."""
+    w = Workload("enc", 2, ((50, 67), (25, 34), (13, 17), (7, 9)), 4484, M=8, P=4, D=32)
+    x = torch_inputs(w, seed=21, loc_mode="wide")
+    dev = cuda_device
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    v16, go16 = x["value"].bfloat16().to(dev), x["grad_out"].bfloat16().to(dev)
+    loc, attn = x["loc"].to(dev), x["attn"].to(dev)
+    out = msda.ms_deform_attn_forward(v16, shapes, start, loc, attn)
+    ref = msda.ms_deform_attn_forward(v16.float(), shapes, start, loc, attn)
+    assert out.dtype == torch.bfloat16
+    assert_close(out.double().cpu().numpy(), ref.double().cpu().numpy(), 1e-2, 1e-2 * rms(ref.double().cpu().numpy()), "out")
+    grads = [torch.empty_like(v16), torch.full_like(loc, float("nan")), torch.full_like(attn, float("nan"))]
+    got = msda.ms_deform_attn_backward(v16, shapes, start, loc, attn, go16, grads=grads, deterministic=det)
+    want = msda.ms_deform_attn_backward(v16.float(), shapes, start, loc, attn, go16.float(), deterministic=det)
+    assert got[1].data_ptr() == grads[1].data_ptr() and got[1].dtype == torch.float32 and got[2].dtype == torch.float32
+    n = lambda t: t.double().cpu().numpy()
+    assert_close(n(got[0]), n(want[0]), 1e-2, 1e-2 * rms(n(want[0])), "grad_value")
+    assert_close_grad_loc(n(got[1]), n(want[1]), x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
+    assert_close_grad(n(got[2]), n(want[2]), 1e-4, "grad_attn")
+    if det:
+        again = msda.ms_deform_attn_backward(v16, shapes, start, loc, attn, go16, deterministic=True)
+        assert all(torch.equal(a, b) for a, b in zip(got, again))
+
+
+def test_mixed_precision_rejections(cuda_device):
+    dev = cuda_device
+    x = torch_inputs(SHAPES[0], seed=3)
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    # fp32 value with 16-bit locations is not a mixed mode
+    with pytest.raises(RuntimeError, match="sampling_loc has dtype"):
+        msda.ms_deform_attn_forward(x["value"].to(dev), shapes, start, x["loc"].bfloat16().to(dev), x["attn"].to(dev))
+    # float64 next to 16-bit value neither
+    with pytest.raises(RuntimeError, match="attn_weight has dtype"):
+        msda.ms_deform_attn_forward(x["value"].bfloat16().to(dev), shapes, start, x["loc"].to(dev), x["attn"].double().to(dev))
+    # grad_output must have value's dtype
+    with pytest.raises(RuntimeError, match="grad_output"):
+        msda.ms_deform_attn_backward(x["value"].bfloat16().to(dev), shapes, start, x["loc"].to(dev), x["attn"].to(dev),
+                                     x["grad_out"].to(dev))
+
+
 @pytest.mark.parametrize("w", [SHAPES[0], SHAPES[1], SHAPES[9]], ids=lambda w: w.name)
 @pytest.mark.parametrize("no_pdl", [0, 1])
 @pytest.mark.parametrize("knob,val", [("force_generic", 1), ("fwd_unroll", 2), ("fwd_unroll", 4), ("bwd_unroll", 2),
