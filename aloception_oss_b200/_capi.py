@@ -116,6 +116,10 @@ def lib() -> ctypes.CDLL:
     L.msda_last_error_string.argtypes = []
     L.msda_forward.restype = i
     L.msda_forward.argtypes = [vp] * 6 + [dp, i, vp]
+    L.msda_forward_workspace_bytes.restype = sz
+    L.msda_forward_workspace_bytes.argtypes = [dp, i]
+    L.msda_forward_ws.restype = i
+    L.msda_forward_ws.argtypes = [vp] * 7 + [sz, dp, i, vp]
     L.msda_forward_host.restype = i
     L.msda_forward_host.argtypes = [vp] * 6 + [dp, i, vp]
     L.msda_backward_workspace_bytes.restype = sz

@@ -29,9 +29,12 @@ struct Io32Scope {
 size_t loc_elt(size_t e) { return (t_io32 & MSDA_LOC_F32) ? sizeof(float) : e; }
 size_t attn_elt(size_t e) { return (t_io32 & MSDA_ATTN_F32) ? sizeof(float) : e; }
 
+// scheduling words of the SM-affine paired forward for the duration of one msda_forward call (caller's workspace), or NULL
+thread_local unsigned long long* t_fwd_sched = nullptr;
+
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0}, g_fwd_pair_mode{0}, g_fwd_pair_ctas{0}, g_fwd_pair_px{0}, g_fwd_pair_py{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -192,6 +195,21 @@ int pick_unroll(int knob, int fallback) {
 // ---------------------------------------------------------------------------------------------
 // forward dispatch
 // ---------------------------------------------------------------------------------------------
+// SM-affine paired forward (msda_fwd_pair_kernel<.., AFFINE>): the schedule for pixel-aligned queries (encoder self-attention)
+bool fwd_affine_shape_ok(const msda_dims& d) {
+  return vec_shape_ok(d) && d.channels == 32 && d.num_levels * d.num_point <= 16 && d.num_heads >= 2 &&
+         (long long)d.spatial_size * d.num_heads * d.channels * 4 <= (1LL << 29);
+}
+bool fwd_affine_wanted(const msda_dims& d) {
+  const int pkm = g_fwd_pair_mode.load(std::memory_order_relaxed);
+  if (!fwd_affine_shape_ok(d) || g_spec_mode.load(std::memory_order_relaxed) == 1) return false;
+  if (pkm == 3) return true;
+  return false;
+}
+int zero_sched(unsigned long long* p, cudaStream_t st) {
+  const cudaError_t e = cudaMemsetAsync(p, 0, sizeof(unsigned long long) * MSDA_SCHED_WORDS, st);
+  return e == cudaSuccess ? 0 : fail("msda_forward(paired, SM-affine): cudaMemsetAsync: %s", cudaGetErrorString(e));
+}
 template <typename T, int D, int MC, bool FUSED = false>
 int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* start, const void* loc, const void* attn,
                    void* out, const msda_dims& d, cudaStream_t st, const void* ref = nullptr, int ref_dim = 0) {
@@ -276,6 +294,42 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const int srk = g_smem_records.load(std::memory_order_relaxed);
   const bool sr = U == 1 && (srk == 2 || (srk == 0 && smem_records_auto(d, sizeof(T))));
   cudaError_t e;
+  // paired forward (two heads of a query per warp; knob "fwd_pair_mode": 0 = auto, 1 = off, 2 = static order, 3 = SM-affine
+  // patch order -- needs the scheduling words of t_fwd_sched)
+  const int pkm = g_fwd_pair_mode.load(std::memory_order_relaxed);
+  // Measured and NOT adopted (profiles/r2_sweep_paired_forward_rejected.jsonl): 24 % fewer warp instructions and, SM-affine,
+  // 53 % L1 hits instead of 22 %, but 99 / 122 us against 95 us on the encoder shape -- kept behind the knob, bit-identical.
+  if constexpr (!FUSED && D == 32) if (U == 1 && (spec_on & 1) && d.num_levels * d.num_point <= 16 && d.num_heads >= 2 && (pkm == 2 || pkm == 3)) {
+    const int hp = (d.num_heads + 1) / 2;
+    const long long items = (long long)d.num_query * hp;
+    const int io_bits = spec_on & 6;
+    if (pkm == 3 && t_fwd_sched != nullptr) {
+      int pxs = g_fwd_pair_px.load(std::memory_order_relaxed), pys = g_fwd_pair_py.load(std::memory_order_relaxed);
+      if (pxs <= 0 || pxs > 6) pxs = 3;
+      if (pys <= 0 || pys > 6) pys = 3;
+      int ctas = g_fwd_pair_ctas.load(std::memory_order_relaxed);
+      if (ctas <= 0 || ctas > 8) ctas = 5;
+      const dim3 grid((unsigned)(sm_count() * ctas)), block(256);
+      if (int rc = zero_sched(t_fwd_sched, st)) return rc;
+#define MSDA_FWDA(SR)                                                                                                      \
+  e = launch_pdl(msda::msda_fwd_pair_kernel<T, D, MC, SR, true>, grid, block, SR ? 24 * block.x : 0, st, false,             \
+                 (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size,           \
+                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, io_bits, t_fwd_sched, pxs, pys)
+      if (sr) MSDA_FWDA(true); else MSDA_FWDA(false);
+#undef MSDA_FWDA
+      return check_pdl_launch(e, "msda_forward(paired, SM-affine)");
+    }
+    const int wpb = 2;
+    const dim3 grid((unsigned)((items + wpb - 1) / wpb), (unsigned)d.batch), block(32 * wpb);
+#define MSDA_FWDQ(SR)                                                                                                      \
+  e = launch_pdl(msda::msda_fwd_pair_kernel<T, D, MC, SR, false>, grid, block, SR ? 24 * block.x : 0, st, false,            \
+                 (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.batch, d.spatial_size,           \
+                 d.num_heads, d.num_levels, d.num_point, inv_p, d.num_query * d.num_heads, io_bits,                         \
+                 (unsigned long long*)nullptr, 0, 0)
+    if (sr) MSDA_FWDQ(true); else MSDA_FWDQ(false);
+#undef MSDA_FWDQ
+    return check_pdl_launch(e, "msda_forward(paired)");
+  }
 #define MSDA_FWD(UU, SR)                                                                                      \
   e = launch_pdl(msda::msda_fwd_sg_kernel<T, D, MC, UU, FUSED, SR>, l.grid, l.block, SR ? 24 * l.block.x : 0, st, pdl, \
                  (const T*)value, shapes, start, (const T*)loc, (const T*)attn, (T*)out, d.spatial_size, d.num_heads,   \
@@ -793,6 +847,10 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "bwd_tile_mode")) return &g_bwd_tile_mode;
   if (!strcmp(name, "bwd_tile_ctas")) return &g_bwd_tile_ctas;
   if (!strcmp(name, "bwd_two_pass")) return &g_bwd_two_pass;
+  if (!strcmp(name, "fwd_pair_mode")) return &g_fwd_pair_mode;
+  if (!strcmp(name, "fwd_pair_ctas")) return &g_fwd_pair_ctas;
+  if (!strcmp(name, "fwd_pair_px")) return &g_fwd_pair_px;
+  if (!strcmp(name, "fwd_pair_py")) return &g_fwd_pair_py;
   if (!strcmp(name, "bwd_chunk_mb")) return &g_bwd_chunk_mb;
   return nullptr;
 }
@@ -811,10 +869,28 @@ int msda_get_tuning(const char* name, int* value) {
   return 0;
 }
 
+size_t msda_forward_workspace_bytes(const msda_dims* dims, int dtype) {
+  if (!dims) return 0;
+  dtype &= ~(MSDA_LOC_F32 | MSDA_ATTN_F32);
+  if (dtype != MSDA_F32 && dtype != MSDA_BF16 && dtype != MSDA_F16) return 0;
+  return fwd_affine_wanted(*dims) ? sizeof(unsigned long long) * MSDA_SCHED_WORDS : 0;
+}
+
 int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
                  const void* sampling_loc, const void* attn_weight, void* output, const msda_dims* dims, int dtype,
                  void* stream) {
+  return msda_forward_ws(value, spatial_shapes, level_start_index, sampling_loc, attn_weight, output, nullptr, 0, dims, dtype, stream);
+}
+
+int msda_forward_ws(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                    const void* sampling_loc, const void* attn_weight, void* output, void* workspace, size_t workspace_bytes,
+                    const msda_dims* dims, int dtype, void* stream) {
   g_err[0] = 0;
+  struct SchedScope {  // scoped: every return path clears it
+    explicit SchedScope(unsigned long long* p) { t_fwd_sched = p; }
+    ~SchedScope() { t_fwd_sched = nullptr; }
+  } sched_scope(workspace != nullptr && workspace_bytes >= sizeof(unsigned long long) * MSDA_SCHED_WORDS && aligned(workspace, 8)
+                    ? (unsigned long long*)workspace : nullptr);
   const int io = dtype & (MSDA_LOC_F32 | MSDA_ATTN_F32);
   dtype &= ~(MSDA_LOC_F32 | MSDA_ATTN_F32);
   if (int rc = validate_dims(dims, dtype)) return rc;

@@ -511,6 +511,96 @@ __device__ __forceinline__ float2 fma2(float w, float2 v, float2 acc) { return _
 // ------------------------------------------------------------------------------------------------
 // VECTOR FORWARD
 // ------------------------------------------------------------------------------------------------
+// ---- the speculative regular window in two halves: the lane's record, and the gather rounds over a range of records ----
+struct SpecRec { unsigned off00, stride; float w00, w01, w10, w11; };
+
+// Geometry of MY sample (see SPEC below) -> record in registers and, SR, in the warp's shared-memory slice.  `extra` is added to
+// the byte offset (the head's column offset when one warp serves two heads from a head-0 base pointer: msda_fwd_pair).
+template <typename T, bool SR>
+__device__ __forceinline__ void spec_record(const SampleParams& sp, bool have, int MD, unsigned extra, SpecRec& r) {
+  const int lane = threadIdx.x & 31;
+  const float fH = (float)sp.H, fW = (float)sp.W;
+  const float y = fma(sp.ly, fH, -0.5f), x = fma(sp.lx, fW, -0.5f);  // same roundings as make_geo
+  const bool inside = have && y > -1.f && x > -1.f && y < fH && x < fW;
+  const float fy = floorf(y), fx = floorf(x);
+  int y0 = (int)fy, x0 = (int)fx;
+  const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
+  float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
+  if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > sp.H - 2) { y0 = sp.H - 2; wy1 = hy; wy0 = 0.f; }
+  if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > sp.W - 2) { x0 = sp.W - 2; wx1 = hx; wx0 = 0.f; }
+  if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; wx0 = 0.f; wx1 = 0.f; }  // (NaN / Inf coordinates land here too)
+  const float a = inside ? sp.a : 0.f;
+  r.w00 = wy0 * wx0 * a; r.w01 = wy0 * wx1 * a; r.w10 = wy1 * wx0 * a; r.w11 = wy1 * wx1 * a;
+  // BYTE offsets from the unit's base pointer (32-bit: the host checks S*M*D*sizeof(T) <= 2^29): a tap pointer is then
+  // one 64-bit add instead of an index add + scale + carry chain
+  r.off00 = (unsigned)((sp.st + y0 * sp.W + x0) * MD) * (unsigned)sizeof(T) + extra;
+  r.stride = (unsigned)(sp.W * MD) * (unsigned)sizeof(T);
+  if constexpr (SR) {
+    extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
+    uint4* rec_a = reinterpret_cast<uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);  // this warp's 32 records
+    float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
+    __syncwarp();
+    rec_a[lane] = make_uint4(r.off00, r.stride, __float_as_uint(r.w00), __float_as_uint(r.w01));
+    rec_b[lane] = make_float2(r.w10, r.w11);
+    __syncwarp();
+  }
+}
+
+// Gather rounds over the records of lanes [k_begin, k_end) (warp-uniform; G * U records per round), accumulating into `acc`.
+template <typename T, int D, int U, bool SR>
+__device__ __forceinline__ void spec_rounds(const T* __restrict__ vb, const SpecRec& r, int MD, int k_begin, int k_end,
+                                            float2 (&acc)[Vec16<T>::N / 2]) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  constexpr int G = 32 / LPR;
+  const int g = (threadIdx.x & 31) / LPR;
+  extern __shared__ __align__(16) unsigned char msda_dyn_smem[];
+  const uint4* rec_a = reinterpret_cast<const uint4*>(msda_dyn_smem) + (threadIdx.x & ~31);
+  const float2* rec_b = reinterpret_cast<const float2*>(reinterpret_cast<const uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
+  const char* vbc = reinterpret_cast<const char*>(vb);
+  const size_t mdb = (size_t)MD * sizeof(T);
+  auto round = [&](int k0) {
+    unsigned off[U], rs[U];
+    float w[U][4];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const int src = k0 + j * G + g;  // < 32
+      if constexpr (SR) {
+        const uint4 ra = rec_a[src];
+        const float2 rb = rec_b[src];
+        off[j] = ra.x; rs[j] = ra.y;
+        w[j][0] = __uint_as_float(ra.z); w[j][1] = __uint_as_float(ra.w); w[j][2] = rb.x; w[j][3] = rb.y;
+      } else {
+        off[j] = __shfl_sync(0xffffffffu, r.off00, src);
+        rs[j] = __shfl_sync(0xffffffffu, r.stride, src);
+        w[j][0] = __shfl_sync(0xffffffffu, r.w00, src);
+        w[j][1] = __shfl_sync(0xffffffffu, r.w01, src);
+        w[j][2] = __shfl_sync(0xffffffffu, r.w10, src);
+        w[j][3] = __shfl_sync(0xffffffffu, r.w11, src);
+      }
+    }
+    uint4 v[U][4];
+#pragma unroll
+    for (int j = 0; j < U; ++j) {
+      const char* t0 = vbc + off[j];
+      const char* t1 = t0 + rs[j];
+      v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + mdb); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + mdb);
+    }
+#pragma unroll
+    for (int j = 0; j < U; ++j)
+#pragma unroll
+      for (int t = 0; t < 4; ++t) {
+        float f[VEC];
+        Vec16<T>::unpack(v[j][t], f);
+#pragma unroll
+        for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
+      }
+  };
+  // (a fully unrolled 4-round variant for L*P = 16 was measured 5 % SLOWER -- 100.1 vs 94.8 us on the encoder shape: the
+  // kernel grows by 70 instructions and ptxas needs 2 spill slots at 40 registers)
+  for (int k0 = k_begin; k0 < k_end; k0 += G * U) round(k0);  // warp-uniform trip count
+}
+
 // Dependent-latency chain per warp: {loc, attn, level shapes} -> 4*U tap rows per group -> shuffles -> store.
 // Register budgets via min-CTAs/SM at 256 threads: U=1 -> 40 regs (48 warps/SM), U=2 -> 64 regs, U=4 -> 80 regs.
 // FUSED: `loc` holds the raw sampling offsets, `attn` the raw attention logits, `ref` the reference points (last dim RD).
@@ -541,70 +631,9 @@ msda_fwd_gather_pass(const T* __restrict__ vb, const SampleParams& sp, bool have
   float2* rec_b = reinterpret_cast<float2*>(reinterpret_cast<uint4*>(msda_dyn_smem) + blockDim.x) + (threadIdx.x & ~31);
 
   if constexpr (SPEC) {
-    const float fH = (float)sp.H, fW = (float)sp.W;
-    const float y = fma(sp.ly, fH, -0.5f), x = fma(sp.lx, fW, -0.5f);  // same roundings as make_geo
-    const bool inside = have && y > -1.f && x > -1.f && y < fH && x < fW;
-    const float fy = floorf(y), fx = floorf(x);
-    int y0 = (int)fy, x0 = (int)fx;
-    const float ly = y - fy, lx = x - fx, hy = 1.f - ly, hx = 1.f - lx;
-    float wy0 = hy, wy1 = ly, wx0 = hx, wx1 = lx;
-    if (y0 < 0) { y0 = 0; wy0 = ly; wy1 = 0.f; } else if (y0 > sp.H - 2) { y0 = sp.H - 2; wy1 = hy; wy0 = 0.f; }
-    if (x0 < 0) { x0 = 0; wx0 = lx; wx1 = 0.f; } else if (x0 > sp.W - 2) { x0 = sp.W - 2; wx1 = hx; wx0 = 0.f; }
-    if (!inside) { y0 = 0; x0 = 0; wy0 = 0.f; wy1 = 0.f; wx0 = 0.f; wx1 = 0.f; }  // (NaN / Inf coordinates land here too)
-    const float a = inside ? sp.a : 0.f;
-    const float w00 = wy0 * wx0 * a, w01 = wy0 * wx1 * a, w10 = wy1 * wx0 * a, w11 = wy1 * wx1 * a;
-    // BYTE offsets from the unit's base pointer (32-bit: the host checks S*M*D*sizeof(T) <= 2^29): a tap pointer is then
-    // one 64-bit add instead of an index add + scale + carry chain
-    const unsigned off00 = (unsigned)((sp.st + y0 * sp.W + x0) * MD) * (unsigned)sizeof(T);
-    const unsigned stride = (unsigned)(sp.W * MD) * (unsigned)sizeof(T);
-    if constexpr (SR) {
-      __syncwarp();
-      rec_a[lane] = make_uint4(off00, stride, __float_as_uint(w00), __float_as_uint(w01));
-      rec_b[lane] = make_float2(w10, w11);
-      __syncwarp();
-    }
-    const char* vbc = reinterpret_cast<const char*>(vb);
-    const size_t mdb = (size_t)MD * sizeof(T);
-    auto round = [&](int k0) {
-      unsigned off[U], rs[U];
-      float w[U][4];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const int src = k0 + j * G + g;  // < 32
-        if constexpr (SR) {
-          const uint4 ra = rec_a[src];
-          const float2 rb = rec_b[src];
-          off[j] = ra.x; rs[j] = ra.y;
-          w[j][0] = __uint_as_float(ra.z); w[j][1] = __uint_as_float(ra.w); w[j][2] = rb.x; w[j][3] = rb.y;
-        } else {
-          off[j] = __shfl_sync(0xffffffffu, off00, src);
-          rs[j] = __shfl_sync(0xffffffffu, stride, src);
-          w[j][0] = __shfl_sync(0xffffffffu, w00, src);
-          w[j][1] = __shfl_sync(0xffffffffu, w01, src);
-          w[j][2] = __shfl_sync(0xffffffffu, w10, src);
-          w[j][3] = __shfl_sync(0xffffffffu, w11, src);
-        }
-      }
-      uint4 v[U][4];
-#pragma unroll
-      for (int j = 0; j < U; ++j) {
-        const char* t0 = vbc + off[j];
-        const char* t1 = t0 + rs[j];
-        v[j][0] = ldg128(t0); v[j][1] = ldg128(t0 + mdb); v[j][2] = ldg128(t1); v[j][3] = ldg128(t1 + mdb);
-      }
-#pragma unroll
-      for (int j = 0; j < U; ++j)
-#pragma unroll
-        for (int t = 0; t < 4; ++t) {
-          float f[VEC];
-          Vec16<T>::unpack(v[j][t], f);
-#pragma unroll
-          for (int i = 0; i < VEC / 2; ++i) acc[i] = fma2(w[j][t], make_float2(f[2 * i], f[2 * i + 1]), acc[i]);
-        }
-    };
-    // (a fully unrolled 4-round variant for L*P = 16 was measured 5 % SLOWER -- 100.1 vs 94.8 us on the encoder shape: the
-    // kernel grows by 70 instructions and ptxas needs 2 spill slots at 40 registers)
-    for (int k0 = 0; k0 < cnt; k0 += G * U) round(k0);  // warp-uniform trip count; lanes >= cnt hold zero-weight records
+    SpecRec r;
+    spec_record<T, SR>(sp, have, MD, 0u, r);
+    spec_rounds<T, D, U, SR>(vb, r, MD, 0, cnt, acc);  // lanes >= cnt hold zero-weight records
     return;
   }
 
@@ -783,8 +812,9 @@ template <typename T, int D, int MC, bool FUSED, bool SR>
 __device__ __noinline__ void
 msda_fwd_unit_flagged(const T* __restrict__ value, const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
                       const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
-                      int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int b, int uq, int m) {
-  msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, b, uq, m, 0);
+                      int S, int M, int L, int P, float inv_p, int QM, const T* __restrict__ ref, int RDf, int b, int uq, int m,
+                      int io = 0) {  // io: bits 1 / 2 of msda_fwd_unit's spec_on word (fp32 locations / weights next to 16-bit value)
+  msda_fwd_unit<T, D, MC, 1, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, b, uq, m, io & 6);
 }
 
 // grid: x = units of one image (one warp each), y = image
@@ -798,6 +828,175 @@ msda_fwd_sg_kernel(const T* __restrict__ value, const int32_t* __restrict__ shap
   int uq, m;  // unit inside image blockIdx.y, its head
   if (!unit_of_warp(M, QM, head_major, uq, m)) return;  // warp-uniform
   msda_fwd_unit<T, D, MC, U, FUSED, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, ref, RDf, (int)blockIdx.y, uq, m, spec_on);
+}
+
+// ------------------------------------------------------------------------------------------------
+// PAIRED forward: one warp serves TWO units -- heads m0 and m0 + 1 of one query -- when L * P <= 16.
+// With 16 samples per unit half of the warp idles through the per-sample prologue (parameter loads, window geometry, record
+// store: ~190 of the ~315 warp instructions a unit costs on the encoder shape, the gather rounds are only ~92).  Here lanes
+// 0..15 hold the samples of head m0 and lanes 16..31 those of head m0 + 1 (their locations / weights are one contiguous
+// 32-sample run in memory), the prologue runs once for both, and the rounds walk records [0, LP) and then [16, 16 + LP).
+// The two heads read different columns of `value`: the records carry the head's column offset, the base pointer is head 0's.
+// Arithmetic per unit is the speculative path of msda_fwd_unit, instruction for instruction: results are bit-identical; a unit
+// whose sums come out non-finite, or a level narrower than 2 pixels, goes to the flagged path (msda_fwd_unit_flagged).
+// ------------------------------------------------------------------------------------------------
+template <typename T, int D, int MC, bool SR>
+__device__ __forceinline__ void
+msda_fwd_pair(const T* __restrict__ value, const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+              const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
+              int S, int M, int L, int P, float inv_p, int QM, int b, int q, int m0, int io) {
+  constexpr int VEC = Vec16<T>::N;
+  constexpr int LPR = D / VEC;
+  constexpr int N_OUT = GroupReduceScatter<VEC, LPR>::N_OUT;
+  const int MD = M * D;
+  const int lane = threadIdx.x & 31;
+  const int cl = lane % LPR;
+  const int LP = L * P;
+  const int h = lane >> 4, s = lane & 15;       // which of the two heads, which of its samples
+  const int nh = min(2, M - m0);                // (an odd head count leaves the last pair with one head)
+  const bool have = s < LP && h < nh;
+  const bool l32 = sizeof(T) != 4 && (io & 2) != 0;
+  const bool a32 = sizeof(T) != 4 && (io & 4) != 0;
+  const int uq = q * M + m0;
+  const long long u0 = (long long)b * QM + uq;  // unit of head m0; head m0 + 1 is unit u0 + 1
+  const long long su = (u0 + (have ? h : 0)) * LP;  // first sample of MY unit
+  const T* __restrict__ u_loc = loc + su * 2 * (l32 ? 2 : 1);
+  const T* __restrict__ u_att = attn + su * (a32 ? 2 : 1);
+  const SampleParams sp = load_params<T>(u_loc, u_att, shapes, start, s, have, inv_p, l32, a32);
+  if (!__all_sync(0xffffffffu, !have || (sp.H >= 2 && sp.W >= 2))) {  // no regular 2 x 2 window on some level (warp-uniform)
+    for (int k = 0; k < nh; ++k)
+      msda_fwd_unit_flagged<T, D, MC, false, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, nullptr, 2, b, uq + k, m0 + k, io);
+    return;
+  }
+  SpecRec r;
+  spec_record<T, SR>(sp, have, MD, (unsigned)((m0 + h) * D) * (unsigned)sizeof(T), r);
+  const T* __restrict__ vb = value + (long long)b * S * MD + cl * VEC;  // head 0: the records hold the head's column
+#pragma unroll 1
+  for (int k = 0; k < nh; ++k) {
+    float2 acc[VEC / 2];
+#pragma unroll
+    for (int i = 0; i < VEC / 2; ++i) acc[i] = make_float2(0.f, 0.f);
+    spec_rounds<T, D, 1, SR>(vb, r, MD, 16 * k, 16 * k + LP, acc);
+    float o[N_OUT];
+    int first;
+    bool owner;
+    msda_fwd_reduce<T, D>(acc, o, first, owner);
+    bool bad = false;
+#pragma unroll
+    for (int i = 0; i < N_OUT; ++i) bad = bad || !(fabsf(o[i]) <= 3.402823466e38f);
+    if (__any_sync(0xffffffffu, bad)) {  // a non-finite value met a zero weight (or is simply there): the flagged path decides
+      msda_fwd_unit_flagged<T, D, MC, false, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, nullptr, 2, b, uq + k, m0 + k, io);
+      if constexpr (SR) __syncwarp();
+    } else if (owner) {
+      store_vals<T, N_OUT>(out + (u0 + k) * D + cl * VEC + first, o);
+    }
+  }
+}
+
+// Scheduling words of the SM-affine variant (device memory, zero before the launch): [0] = next chunk to hand out,
+// [1 + smid] = the chunk SM `smid` is working on ((chunk + 1) << 32 | next position in it).
+#define MSDA_SCHED_WORDS 1025
+#define MSDA_SCHED_DONE 0xffffffffu
+
+// grid (static):  x = query-pairs of one image (one warp each), y = image.
+// grid (AFFINE):  persistent, x = SMs * CTAs per SM.  For pixel-aligned queries (encoder self-attention: Lq == S, query i is pixel
+//   i of the pyramid and samples around its own position) the warps of ONE SM work through PY x PX patches of queries, all head
+//   pairs of a patch in turn, so the taps of neighbouring queries are served by that SM's L1 instead of each going to L2 (the
+//   unit-ordered kernel: 21 % L1 hits, every miss costs a fill cycle on the L1 data stage it shares with the reads).  A chunk = one
+//   patch of one image = PY*PX*ceil(M/2) warp items; the SM's warps take items of its current chunk with one atomicAdd each
+//   (issued before the previous item's gathers, so its latency is hidden) and the warp that draws the last one fetches the next
+//   chunk from the global counter: SMs stay on their patch whatever the warps' individual speeds are, the chunks balance the SMs
+//   dynamically.  Pure scheduling: every (image, query, head) is processed exactly once whatever the level shapes are (queries
+//   beyond the level grids come as plain-order chunks); if the queries are not pixel-aligned only locality is lost.
+template <typename T, int D, int MC, bool SR, bool AFFINE>
+__global__ void __launch_bounds__(256, AFFINE ? 5 : 6)
+msda_fwd_pair_kernel(const T* __restrict__ value, const int32_t* __restrict__ shapes, const int32_t* __restrict__ start,
+                     const T* __restrict__ loc, const T* __restrict__ attn, T* __restrict__ out,
+                     int N, int S, int Mrt, int L, int P, float inv_p, int QM, int io, unsigned long long* __restrict__ sched,
+                     int pxs, int pys) {
+  const int M = MC > 0 ? MC : Mrt;
+  const int HP = (M + 1) >> 1;  // head pairs per query
+  const int Lq = QM / M;
+  if constexpr (!AFFINE) {
+    const long long item = (long long)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+    if (item >= (long long)Lq * HP) return;  // warp-uniform
+    const int q = (int)(item / HP), hp = (int)(item - (long long)q * HP);
+    msda_fwd_pair<T, D, MC, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, (int)blockIdx.y, q, 2 * hp, io);
+  } else {
+    const int lane = threadIdx.x & 31;
+    const int PX = 1 << pxs, PY = 1 << pys;
+    const unsigned C = (unsigned)(HP << (pxs + pys));  // items per chunk
+    // patches per image over the level grids, queries they cover (warp-uniform, L <= a few levels)
+    int patches = 0, pixels = 0;
+    for (int l = 0; l < L; ++l) {
+      const int H = __ldg(shapes + 2 * l), W = __ldg(shapes + 2 * l + 1);
+      patches += ((H + PY - 1) >> pys) * ((W + PX - 1) >> pxs);
+      pixels += H * W;
+    }
+    pixels = min(pixels, Lq);
+    const long long grid_chunks = (long long)patches * N;
+    const int tail_q = Lq - pixels;  // queries beyond the level grids: chunks of PY*PX queries in plain order
+    const int tail_per_image = (tail_q + (1 << (pxs + pys)) - 1) >> (pxs + pys);
+    const long long n_chunks = grid_chunks + (long long)tail_per_image * N;
+    unsigned smid;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+    unsigned long long* cur = sched + 1 + (smid & 1023u);
+    // one ticket of this SM's current chunk: lane 0 draws, the value is broadcast only where it is needed (`bcast`), so the
+    // draw for the NEXT item is in flight while this one is processed
+    auto draw = [&]() -> unsigned long long { return lane == 0 ? atomicAdd(cur, 1ull) : 0ull; };
+    auto bcast = [&](unsigned long long v) -> unsigned long long { return __shfl_sync(0xffffffffu, v, 0); };
+    unsigned long long t_raw = draw();
+    for (;;) {
+      unsigned long long t = bcast(t_raw);
+      unsigned hi = (unsigned)(t >> 32), pos = (unsigned)t;
+      if (hi == MSDA_SCHED_DONE) break;
+      if (hi == 0 || pos >= C) {  // no chunk installed yet / the chunk is used up
+        if (hi == 0 ? pos != 0 : pos != C) {  // ... and another warp (the one that drew ticket 0 / C) is fetching the next one
+          __nanosleep(200);
+          t_raw = draw();
+          continue;
+        }
+        unsigned long long nc = 0;  // I drew the first ticket past the end (or the very first one): fetch the next chunk
+        if (lane == 0) {
+          nc = atomicAdd(sched, 1ull);
+          atomicExch(cur, nc >= (unsigned long long)n_chunks ? ((unsigned long long)MSDA_SCHED_DONE << 32) : (((nc + 1) << 32) | 1ull));
+        }
+        nc = __shfl_sync(0xffffffffu, nc, 0);
+        if (nc >= (unsigned long long)n_chunks) break;
+        hi = (unsigned)nc + 1;
+        pos = 0;
+      }
+      const unsigned long long t_next = draw();  // in flight while this item is processed
+      const long long c = (long long)hi - 1;
+      const int hp = (int)(pos >> (pxs + pys)), rr = (int)(pos & ((1u << (pxs + pys)) - 1));
+      int b, q = -1;
+      if (c < grid_chunks) {
+        b = (int)(c / patches);
+        int patch = (int)(c - (long long)b * patches);
+        int l = 0, H = 0, W = 0, npx = 1, first = 0;  // first = index of the level's first query
+        for (; l < L; ++l) {
+          H = __ldg(shapes + 2 * l);
+          W = __ldg(shapes + 2 * l + 1);
+          npx = (W + PX - 1) >> pxs;
+          const int np = ((H + PY - 1) >> pys) * npx;
+          if (patch < np) break;
+          patch -= np;
+          first += H * W;
+        }
+        const int prow = patch / npx;
+        const int y = (prow << pys) + (rr >> pxs), x = ((patch - prow * npx) << pxs) + (rr & (PX - 1));
+        if (y < H && x < W) q = first + y * W + x;
+        if (q >= Lq) q = -1;
+      } else {
+        const long long ct = c - grid_chunks;
+        b = (int)(ct / tail_per_image);
+        q = pixels + (((int)(ct - (long long)b * tail_per_image)) << (pxs + pys)) + rr;
+        if (q >= Lq) q = -1;
+      }
+      if (q >= 0) msda_fwd_pair<T, D, MC, SR>(value, shapes, start, loc, attn, out, S, M, L, P, inv_p, QM, b, q, 2 * hp, io);
+      t_raw = t_next;
+    }
+  }
 }
 
 // PATCH-ORDERED forward for pixel-aligned queries (encoder self-attention: Lq == S, query i is pixel i of the pyramid

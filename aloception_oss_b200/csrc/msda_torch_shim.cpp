@@ -97,9 +97,14 @@ at::Tensor forward_cuda(const at::Tensor& value, const at::Tensor& spatial_shape
   const at::Tensor shapes = meta_i32(spatial_shapes, "spatial_shapes"), start = meta_i32(level_start_index, "level_start_index");
   const c10::cuda::CUDAGuard guard(value.device());
   at::Tensor out = at::empty({d.batch, d.num_query, (int64_t)d.num_heads * d.channels}, value.options());
-  const int rc = msda_forward(ptr(value), (const int32_t*)ptr(shapes), (const int32_t*)ptr(start), ptr(sampling_loc), ptr(attn_weight),
-                              const_cast<void*>(ptr(out)), &d, io_dtype(value, sampling_loc, attn_weight),
-                              (void*)at::cuda::getCurrentCUDAStream().stream());
+  const int dt = io_dtype(value, sampling_loc, attn_weight);
+  // scheduling words for the schedules that need them (msda_forward_ws): 0 bytes -- and no allocation -- for every default path
+  const size_t ws_bytes = msda_forward_workspace_bytes(&d, dt);
+  at::Tensor ws;
+  if (ws_bytes) ws = at::empty({(int64_t)ws_bytes}, value.options().dtype(at::kByte));
+  const int rc = msda_forward_ws(ptr(value), (const int32_t*)ptr(shapes), (const int32_t*)ptr(start), ptr(sampling_loc), ptr(attn_weight),
+                                 const_cast<void*>(ptr(out)), ws_bytes ? ws.data_ptr() : nullptr, ws_bytes, &d, dt,
+                                 (void*)at::cuda::getCurrentCUDAStream().stream());
   TORCH_CHECK(rc == 0, "msda_forward failed: ", msda_last_error_string());
   return out;
 }

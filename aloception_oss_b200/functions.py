@@ -170,9 +170,14 @@ def ms_deform_attn_forward(value, spatial_shapes, level_start_index, sampling_lo
     start = _meta_i32(level_start_index, "level_start_index")
     oshape = (dims.batch, dims.num_query, dims.num_heads * dims.channels)
     out = torch.empty(oshape, dtype=value.dtype, device=value.device) if out is None else _check_out(out, oshape, value, "out")
+    L = _capi.lib()
+    dt = _io_dtype(value, sampling_loc, attn_weight)
+    # scheduling words for encoder-sized calls (msda_forward_ws): 0 bytes -- and no allocation -- for everything else
+    ws_bytes = L.msda_forward_workspace_bytes(ctypes.byref(dims), dt)
+    ws = torch.empty((ws_bytes,), dtype=torch.uint8, device=value.device) if ws_bytes else None
     with _on_device(value) as stream:
-        rc = _capi.lib().msda_forward(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight),
-                                      _ptr(out), ctypes.byref(dims), _io_dtype(value, sampling_loc, attn_weight), stream)
+        rc = L.msda_forward_ws(_ptr(value), _ptr(shapes), _ptr(start), _ptr(sampling_loc), _ptr(attn_weight), _ptr(out),
+                               _ptr(ws) if ws is not None else None, ws_bytes, ctypes.byref(dims), dt, stream)
     if rc != 0:
         raise RuntimeError("msda_forward failed: " + _capi.last_error())
     return out

@@ -77,6 +77,20 @@ int msda_forward(const void* value, const int32_t* spatial_shapes, const int32_t
                  int dtype, void* stream);
 
 /*
+ * Forward with caller-provided scratch.  Same operation and results (bit for bit) as msda_forward; `workspace` -- device
+ * memory of at least msda_forward_workspace_bytes() bytes, 8-byte aligned, owned by this call until it completes on `stream`,
+ * contents irrelevant -- lets the library pick schedules that need a few scheduling words on the device: the SM-affine paired
+ * forward for encoder-sized calls (queries = the pixels of the pyramid, Lq == S).  The library never
+ * allocates device memory itself (allocation is not capturable in a CUDA graph and not stream-ordered); with workspace == NULL
+ * (or too small) the call is msda_forward.  msda_forward_workspace_bytes is a pure host function: 0 when no such schedule would
+ * be chosen for this problem (every decoder-sized call), a few KB otherwise.
+ */
+size_t msda_forward_workspace_bytes(const msda_dims* dims, int dtype);
+int msda_forward_ws(const void* value, const int32_t* spatial_shapes, const int32_t* level_start_index,
+                    const void* sampling_loc, const void* attn_weight, void* output, void* workspace,
+                    size_t workspace_bytes, const msda_dims* dims, int dtype, void* stream);
+
+/*
  * Bytes of scratch `msda_backward` needs for this problem (0 for MSDA_F32 / MSDA_F64; an fp32
  * accumulation image of grad_value for the 16-bit types).
  */
@@ -209,6 +223,10 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *                      images of at most this size (zero-fill + scatter per group), so that every grad_value line meets DRAM once
  *   "bwd_two_pass"     0=auto, 1=unit-ordered backward scatters each round right behind its gather, 2=all gather rounds, then
  *                      the fence behind the zero-fill, then all scatter rounds
+ *   "fwd_pair_mode"    0=auto (= off), 1=off, 2=paired forward: one warp serves two heads of a query (L*P <= 16, D = 32; 24 % fewer
+ *                      warp instructions), 3=paired + SM-affine patch order for pixel-aligned queries (needs msda_forward_ws'
+ *                      workspace; else 2).  Bit-identical results; measured slower than the unit-ordered forward (profiles/)
+ *   "fwd_pair_px/py"   log2 of the SM-affine patch size in queries (default 3, 3 = 8 x 8); "fwd_pair_ctas": its CTAs per SM (5)
  */
 int msda_set_tuning(const char* name, int value);
 int msda_get_tuning(const char* name, int* value);

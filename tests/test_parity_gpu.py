@@ -24,7 +24,8 @@ def _ops(cuda_device):
     msda.load_ops()
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
               "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
-              "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas", "bwd_two_pass"):
+              "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas", "bwd_two_pass", "fwd_pair_mode", "fwd_pair_px",
+              "fwd_pair_py", "fwd_pair_ctas"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -274,6 +275,78 @@ def test_speculative_gather_is_the_same_function(levels, lq, M, P, poison, dtype
     assert np.array_equal(got, base, equal_nan=True)
     if poison is not None and lq >= 300:
         assert np.isfinite(base).any() and not np.isfinite(base).all()
+
+
+@pytest.mark.parametrize("levels,lq,M,P", [
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 392, 8, 4),   # pixel-aligned queries (Lq == S), L*P = 16: the encoder case
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 450, 8, 4),   # more queries than pixels: the SM-affine order's plain-order tail
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 300, 8, 4),   # fewer queries than pixels: its level grids overshoot Lq
+    (((16, 16), (8, 8)), 320, 5, 4),                       # odd run-time head count: the last pair of a query has one head
+    (((16, 16), (8, 8), (4, 4)), 336, 8, 3),               # L*P = 9: ragged rounds, idle lanes in both halves
+    (((9, 11),), 99, 2, 2),                                # one level, one pair
+    (((12, 1), (5, 7)), 47, 4, 4),                         # a level narrower than 2 pixels: no regular window, flagged path
+])
+@pytest.mark.parametrize("poison", [None, float("nan")], ids=["finite", "nan"])
+@pytest.mark.parametrize("dtype", [None, torch.bfloat16, torch.float16, "mixed"], ids=["f32", "bf16", "f16", "bf16+f32loc"])
+@pytest.mark.parametrize("mode,px,py", [(2, 0, 0), (3, 3, 3), (3, 2, 1), (3, 1, 4)], ids=["static", "affine8x8", "affine4x2", "affine2x16"])
+def test_paired_forward_is_the_same_function(levels, lq, M, P, poison, dtype, mode, px, py, cuda_device):
+    """The paired forward (one warp = two heads of a query; knob fwd_pair_mode = 2) and its SM-affine patch order (= 3, scheduling
+    words from msda_forward_ws' workspace) are pure re-schedulings of the unit-ordered forward: bit-identical outputs, every
+    (image, query, head) written exactly once whatever the level shapes, including units that fall back to the flagged path."""
+    w = Workload("pair_small", 3, levels, lq, M=M, P=P, D=32)
+    x = torch_inputs(w, seed=37, loc_mode="wide")
+    if poison is not None:
+        x["value"][:, ::29] = poison
+    dev = cuda_device
+    vt = torch.bfloat16 if dtype == "mixed" else dtype
+    f = lambda t, d: (t.to(d) if d is not None else t).to(dev)
+    lt = None if dtype == "mixed" else dtype
+    value, loc, attn = f(x["value"], vt), f(x["loc"], lt), f(x["attn"], lt)
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    _capi.set_tuning("spec_mode", 2)
+    _capi.set_tuning("fwd_pair_mode", 1)
+    base = msda.ms_deform_attn_forward(value, shapes, start, loc, attn)
+    n0 = _capi.kernel_launch_count()
+    _capi.set_tuning("fwd_pair_mode", mode)
+    _capi.set_tuning("fwd_pair_px", px)
+    _capi.set_tuning("fwd_pair_py", py)
+    out = torch.full_like(base, float("inf"))  # poisoned buffer: an unwritten row would show
+    got = msda.ms_deform_attn_forward(value, shapes, start, loc, attn, out=out)
+    torch.cuda.synchronize()
+    for k in ("fwd_pair_mode", "fwd_pair_px", "fwd_pair_py", "spec_mode"):
+        _capi.set_tuning(k, 0)
+    assert _capi.kernel_launch_count() == n0 + 1
+    assert torch.equal(torch.nan_to_num(got.float(), nan=12345.0), torch.nan_to_num(base.float(), nan=12345.0))
+    if poison is not None:
+        assert torch.isfinite(base.float()).any() and not torch.isfinite(base.float()).all()
+
+
+def test_paired_forward_through_the_registered_op_and_under_graph_capture(cuda_device):
+    """fwd_pair_mode = 3 through torch.ops (C++ shim or Python registration: both query msda_forward_workspace_bytes and pass a
+    caching-allocator buffer to msda_forward_ws) and inside a CUDA graph (the scheduling words are zeroed by a memset node)."""
+    w = WORKLOADS["ENC"]
+    x = device_inputs(w, seed=9, device=cuda_device, loc_mode="raster")
+    args = (x["value"], x["shapes"], x["start"], x["loc"], x["attn"], 64)
+    base = torch.ops.alonet_custom.ms_deform_attn_forward(*args)
+    _capi.set_tuning("fwd_pair_mode", 3)
+    try:
+        dims = _capi.MsdaDims(w.N, w.S, w.M, w.D, w.L, w.Lq, w.P)
+        import ctypes
+        assert _capi.lib().msda_forward_workspace_bytes(ctypes.byref(dims), _capi.F32) > 0
+        got = torch.ops.alonet_custom.ms_deform_attn_forward(*args)
+        assert torch.equal(got, base)
+        g = torch.cuda.CUDAGraph()
+        static = [None]
+        with torch.cuda.graph(g):
+            static[0] = torch.ops.alonet_custom.ms_deform_attn_forward(*args)
+        for _ in range(3):
+            g.replay()
+        torch.cuda.synchronize()
+        assert torch.equal(static[0], base)
+    finally:
+        _capi.set_tuning("fwd_pair_mode", 0)
+    import ctypes
+    assert _capi.lib().msda_forward_workspace_bytes(ctypes.byref(dims), _capi.F32) == 0  # default: no schedule needs scratch
 
 
 @pytest.mark.parametrize("levels,lq,M,P", [
