@@ -42,6 +42,9 @@ def main():
     ap.add_argument("--warmup", type=int, default=2)
     ap.add_argument("--boxes", type=int, default=7, help="train: target boxes per image")
     ap.add_argument("--no-optimizer", action="store_true")
+    ap.add_argument("--autocast", default="off", choices=["off", "bf16", "f16"],
+                    help="run the model under torch.autocast: the reference module then hands the operator 16-bit value next to fp32 "
+                         "sampling locations / attention weights (MSDA_LOC_F32 | MSDA_ATTN_F32)")
     ap.add_argument("--unit-bwd", action="store_true", help="(knob) keep the unit-ordered backward for the encoder calls")
     ap.add_argument("--tile-bwd", action="store_true", help="(knob) tile-binned backward for the encoder calls")
     args = ap.parse_args()
@@ -97,6 +100,8 @@ def main():
             r = fn(value, *a, **k)
             e1.record()
             loc = a[2]
+            op_dtypes.add("value %s, sampling_loc %s, attn_weight %s" % (str(value.dtype).replace("torch.", ""), str(loc.dtype).replace("torch.", ""),
+                                                                         str(a[3].dtype).replace("torch.", "")))
             log.append((kind, e0, e1, loc.shape[0] * loc.shape[1] * loc.shape[2] * loc.shape[3] * loc.shape[4]))
             return r
         return wrap
@@ -129,11 +134,28 @@ def main():
         frames.append(f)
     batch = aloscene.Frame.batch_list(frames).to(dev)
 
+    import contextlib
+
+    def cast():
+        if args.autocast == "off":
+            return contextlib.nullcontext()
+        return torch.autocast("cuda", dtype=torch.bfloat16 if args.autocast == "bf16" else torch.float16)
+
+    def to_f32(o):
+        if torch.is_tensor(o):
+            return o.float() if o.is_floating_point() else o
+        if isinstance(o, dict):
+            return {k: to_f32(v) for k, v in o.items()}
+        if isinstance(o, (list, tuple)):
+            return type(o)(to_f32(v) for v in o)
+        return o
+
+    op_dtypes = set()
     if args.mode == "infer":
         model.eval()
 
         def step():
-            with torch.no_grad():
+            with torch.no_grad(), cast():
                 out = model(batch)
             return out["pred_logits"]
     else:
@@ -151,7 +173,10 @@ def main():
             else:
                 for p in model.parameters():
                     p.grad = None
-            out = net(batch)
+            with cast():
+                out = net(batch)
+            if args.autocast != "off":  # the criterion (focal / L1 / GIoU losses, scipy matcher) runs in fp32, outside autocast
+                out = to_f32(out)
             loss, _ = crit(out, batch)
             loss.backward()
             if opt is not None:
@@ -195,7 +220,8 @@ def main():
             "bench": "reference DeformableDetrR50 (unmodified alonet classes) on the B200 operator",
             "config": ("BASELINE.json configs[3]: inference, B=%d synthetic %dx%d, batch-sharded" % (images, args.height, args.width)) if args.mode == "infer"
             else ("BASELINE.json configs[4]: training step fwd + criterion + bwd%s, B=%d (%d per GPU), DDP" % ("" if args.no_optimizer else " + AdamW", images, n_local)),
-            "mode": args.mode, "n_gpus": world, "global_batch": images, "per_gpu_batch": n_local, "dtype": "f32",
+            "mode": args.mode, "n_gpus": world, "global_batch": images, "per_gpu_batch": n_local,
+            "dtype": "f32" if args.autocast == "off" else "torch.autocast(%s)" % args.autocast, "operator_dtypes": sorted(op_dtypes),
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": round(ms, 3), "ms_per_step_wall": round(wall, 3),
             "images_per_s": round(images / (ms * 1e-3), 2),
             "params_M": round(n_params / 1e6, 2), "msdeformattn_modules": n_attn, "module_class": type(attn_cls).__module__ + "." + type(attn_cls).__name__,
