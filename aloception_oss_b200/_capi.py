@@ -45,7 +45,7 @@ def needs_build() -> bool:
     if not os.path.exists(LIB_PATH):
         return True
     t = os.path.getmtime(LIB_PATH)
-    deps = sources() + [os.path.join(CSRC, "msda_kernels.cuh"), os.path.join(CSRC, "msda_bwd_tile.cuh"), HEADER]
+    deps = sources() + [os.path.join(CSRC, "msda_kernels.cuh"), os.path.join(CSRC, "msda_bwd_tile.cuh"), os.path.join(CSRC, "msda_fwd_win.cuh"), HEADER]
     return any(os.path.getmtime(d) > t for d in deps)
 
 

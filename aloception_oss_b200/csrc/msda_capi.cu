@@ -16,6 +16,7 @@
 
 #include "msda_kernels.cuh"
 #include "msda_bwd_tile.cuh"
+#include "msda_fwd_win.cuh"
 
 namespace {
 
@@ -34,7 +35,7 @@ thread_local unsigned long long* t_fwd_sched = nullptr;
 
 thread_local char g_err[512] = "";
 std::atomic<unsigned long long> g_launches{0};
-std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0}, g_fwd_pair_mode{0}, g_fwd_pair_ctas{0}, g_fwd_pair_px{0}, g_fwd_pair_py{0};
+std::atomic<int> g_force_generic{0}, g_fwd_unroll{0}, g_bwd_unroll{0}, g_warps_per_block{0}, g_no_pdl{0}, g_head_major{0}, g_smem_records{0}, g_patch_mode{0}, g_patch_px{0}, g_patch_py{0}, g_patch_ctas{0}, g_staged_mode{0}, g_staged_kb{0}, g_staged_warps{0}, g_staged_variant{0}, g_zero_ctas{0}, g_zero_threads{0}, g_zero_mode{0}, g_zero_chunk_kb{0}, g_spec_mode{0}, g_bwd_tile_mode{0}, g_bwd_tile_ctas{0}, g_bwd_two_pass{0}, g_fwd_pair_mode{0}, g_fwd_pair_ctas{0}, g_fwd_pair_px{0}, g_fwd_pair_py{0}, g_fwd_win_mode{0}, g_fwd_win_ctas{0};
 
 int fail(const char* fmt, ...) {
   va_list ap;
@@ -294,6 +295,28 @@ int launch_fwd_vec(const void* value, const int32_t* shapes, const int32_t* star
   const int srk = g_smem_records.load(std::memory_order_relaxed);
   const bool sr = U == 1 && (srk == 2 || (srk == 0 && smem_records_auto(d, sizeof(T))));
   cudaError_t e;
+  // windowed forward for pixel-aligned queries (msda_fwd_win.cuh; knob "fwd_win_mode": 0 = auto, 1 = off, 2 = on)
+  const int wkm = g_fwd_win_mode.load(std::memory_order_relaxed);
+  if constexpr (!FUSED && D == 32 && sizeof(T) == 4) if (wkm == 2 && io == 0 && d.num_levels * d.num_point <= 16 && d.num_levels <= MSDA_WIN_LEVELS &&
+                                                         (long long)d.spatial_size * d.num_heads * d.channels * 4 <= (1LL << 29)) {
+    using Cfg = msda::FwdWinCfg<32, 3, 3, 704>;
+    auto kern = msda::msda_fwd_win_kernel<Cfg, MC>;
+    static std::atomic<int> smem_set[64];
+    int dev_ = 0;
+    cudaGetDevice(&dev_);
+    std::atomic<int>& slot = smem_set[dev_ & 63];
+    if (!slot.load(std::memory_order_relaxed)) {
+      const cudaError_t ae = cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)Cfg::SMEM);
+      if (ae != cudaSuccess) return fail("msda_forward(windowed): cudaFuncSetAttribute(%zu B): %s", (size_t)Cfg::SMEM, cudaGetErrorString(ae));
+      slot.store(1, std::memory_order_relaxed);
+    }
+    int ctas = g_fwd_win_ctas.load(std::memory_order_relaxed);
+    if (ctas <= 0 || ctas > 4) ctas = 2;
+    e = launch_pdl(kern, dim3((unsigned)(sm_count() * ctas)), dim3(Cfg::THREADS), Cfg::SMEM, st, false, (const float*)value, shapes, start,
+                   (const float*)loc, (const float*)attn, (float*)out, d.batch, d.spatial_size, d.num_heads, d.num_levels, d.num_point,
+                   inv_p, d.num_query * d.num_heads);
+    return check_pdl_launch(e, "msda_forward(windowed)");
+  }
   // paired forward (two heads of a query per warp; knob "fwd_pair_mode": 0 = auto, 1 = off, 2 = static order, 3 = SM-affine
   // patch order -- needs the scheduling words of t_fwd_sched)
   const int pkm = g_fwd_pair_mode.load(std::memory_order_relaxed);
@@ -847,6 +870,8 @@ static std::atomic<int>* knob(const char* name) {
   if (!strcmp(name, "bwd_tile_mode")) return &g_bwd_tile_mode;
   if (!strcmp(name, "bwd_tile_ctas")) return &g_bwd_tile_ctas;
   if (!strcmp(name, "bwd_two_pass")) return &g_bwd_two_pass;
+  if (!strcmp(name, "fwd_win_mode")) return &g_fwd_win_mode;
+  if (!strcmp(name, "fwd_win_ctas")) return &g_fwd_win_ctas;
   if (!strcmp(name, "fwd_pair_mode")) return &g_fwd_pair_mode;
   if (!strcmp(name, "fwd_pair_ctas")) return &g_fwd_pair_ctas;
   if (!strcmp(name, "fwd_pair_px")) return &g_fwd_pair_px;

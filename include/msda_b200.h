@@ -226,6 +226,9 @@ int msda_im2col_inference(void* stream, const void* data_value, const void* data
  *   "fwd_pair_mode"    0=auto (= off), 1=off, 2=paired forward: one warp serves two heads of a query (L*P <= 16, D = 32; 24 % fewer
  *                      warp instructions), 3=paired + SM-affine patch order for pixel-aligned queries (needs msda_forward_ws'
  *                      workspace; else 2).  Bit-identical results; measured slower than the unit-ordered forward (profiles/)
+ *   "fwd_win_mode"     0=auto (= off), 1=off, 2=windowed forward for pixel-aligned queries (fp32, D = 32, L*P <= 16): a CTA stages the
+ *                      per-level boxes of `value` its 8x8 query tile samples in shared memory and gathers from there; levels whose
+ *                      box exceeds the budget stay on the global path.  Bit-identical; measured slower (profiles/)
  *   "fwd_pair_px/py"   log2 of the SM-affine patch size in queries (default 3, 3 = 8 x 8); "fwd_pair_ctas": its CTAs per SM (5)
  */
 int msda_set_tuning(const char* name, int value);

@@ -25,7 +25,7 @@ def _ops(cuda_device):
     for k in ("force_generic", "fwd_unroll", "bwd_unroll", "warps_per_block", "no_pdl", "head_major", "smem_records", "patch_mode", "patch_px",
               "patch_py", "patch_ctas", "staged_mode", "staged_kb", "staged_warps", "staged_variant", "zero_mode", "zero_ctas",
               "zero_threads", "zero_chunk_kb", "spec_mode", "bwd_tile_mode", "bwd_tile_ctas", "bwd_two_pass", "fwd_pair_mode", "fwd_pair_px",
-              "fwd_pair_py", "fwd_pair_ctas"):
+              "fwd_pair_py", "fwd_pair_ctas", "fwd_win_mode", "fwd_win_ctas"):
         _capi.set_tuning(k, 0)
     yield
 
@@ -319,6 +319,49 @@ def test_paired_forward_is_the_same_function(levels, lq, M, P, poison, dtype, mo
     assert torch.equal(torch.nan_to_num(got.float(), nan=12345.0), torch.nan_to_num(base.float(), nan=12345.0))
     if poison is not None:
         assert torch.isfinite(base.float()).any() and not torch.isfinite(base.float()).all()
+
+
+@pytest.mark.parametrize("levels,lq,M,P", [
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 392, 8, 4),   # pixel-aligned queries (Lq == S), L*P = 16: the encoder case
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 450, 8, 4),   # more queries than pixels: plain-order tail
+    (((13, 21), (7, 11), (4, 6), (2, 3)), 300, 8, 4),   # fewer queries than pixels: the level grids overshoot Lq
+    (((40, 40), (20, 20)), 2000, 3, 4),                    # run-time head count; boxes of the fine level overflow the window budget
+    (((16, 16), (8, 8), (4, 4)), 336, 8, 3),               # L*P = 9
+    (((12, 1), (5, 7)), 47, 4, 4),                         # a level narrower than 2 pixels: flagged path
+])
+@pytest.mark.parametrize("poison", [None, float("nan")], ids=["finite", "nan"])
+@pytest.mark.parametrize("mode", ["raster-ish", "wide"])
+def test_windowed_forward_is_the_same_function(levels, lq, M, P, poison, mode, cuda_device):
+    """The windowed forward (msda_fwd_win.cuh, knob fwd_win_mode = 2: per-level boxes of `value` staged in shared memory per
+    query tile) is a pure re-scheduling of the unit-ordered forward: bit-identical outputs for local and non-local sampling
+    locations, staged and unstaged levels, every (image, query, head) written exactly once."""
+    w = Workload("win_small", 3, levels, lq, M=M, P=P, D=32)
+    x = torch_inputs(w, seed=41, loc_mode="wide")
+    if mode == "raster-ish":  # locations near the query's own pixel (as far as the query is a pixel), +-3 px
+        S = sum(h * wd for h, wd in levels)
+        ref = []
+        for h, wd in levels:
+            ys, xs = torch.meshgrid((torch.arange(h) + 0.5) / h, (torch.arange(wd) + 0.5) / wd, indexing="ij")
+            ref.append(torch.stack([xs.reshape(-1), ys.reshape(-1)], -1))
+        ref = torch.cat(ref, 0)
+        ref = torch.cat([ref, torch.rand(max(0, lq - S), 2)], 0)[:lq]
+        wh = x["shapes"].flip(-1).float().view(1, 1, 1, len(levels), 1, 2)
+        x["loc"] = (ref.view(1, lq, 1, 1, 1, 2) + (torch.rand(x["loc"].shape) - 0.5) * 6.0 / wh).contiguous()
+    if poison is not None:
+        x["value"][:, ::29] = poison
+    dev = cuda_device
+    value, loc, attn = x["value"].to(dev), x["loc"].to(dev), x["attn"].to(dev)
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    _capi.set_tuning("fwd_win_mode", 1)
+    base = msda.ms_deform_attn_forward(value, shapes, start, loc, attn)
+    _capi.set_tuning("fwd_win_mode", 2)
+    out = torch.full_like(base, float("inf"))
+    got = msda.ms_deform_attn_forward(value, shapes, start, loc, attn, out=out)
+    torch.cuda.synchronize()
+    _capi.set_tuning("fwd_win_mode", 0)
+    assert torch.equal(torch.nan_to_num(got, nan=12345.0), torch.nan_to_num(base, nan=12345.0))
+    if poison is not None:
+        assert torch.isfinite(base).any() and not torch.isfinite(base).all()
 
 
 def test_paired_forward_through_the_registered_op_and_under_graph_capture(cuda_device):
