@@ -54,7 +54,7 @@ struct WinLevels {
   int H[MSDA_WIN_LEVELS], W[MSDA_WIN_LEVELS], st[MSDA_WIN_LEVELS], first[MSDA_WIN_LEVELS];
   int xmin[MSDA_WIN_LEVELS], xmax[MSDA_WIN_LEVELS], ymin[MSDA_WIN_LEVELS], ymax[MSDA_WIN_LEVELS];
   int wbase[MSDA_WIN_LEVELS], ww[MSDA_WIN_LEVELS], staged[MSDA_WIN_LEVELS], rows[MSDA_WIN_LEVELS];
-  int total_rows, pad[3];
+  int total_rows, t_m, t_b, t_level, t_y, t_x, pad[2];
 };
 
 template <typename Cfg, int MC>
@@ -102,26 +102,33 @@ msda_fwd_win_kernel(const float* __restrict__ value, const int32_t* __restrict__
   const long long n_tiles = (long long)patches * NM;
 
   for (long long tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-    // ---- tile -> (patch, image, head) -> level, origin ----
-    const int m = (int)(tile % M);
-    const long long rest = tile / M;
-    const int b = (int)(rest % N);
-    int patch = (int)(rest / N);
-    int tl = 0, tH = 0, tW = 0, npx = 1, tfirst = 0;
-    for (; tl < L; ++tl) {
-      tH = lv->H[tl]; tW = lv->W[tl]; tfirst = lv->first[tl];
-      npx = (tW + TX - 1) >> Cfg::TXS;
-      const int np = ((tH + TY - 1) >> Cfg::TYS) * npx;
-      if (patch < np) break;
-      patch -= np;
+    // ---- tile -> (patch, image, head) -> level, origin: one thread decodes, everybody reads ----
+    if (threadIdx.x == 0) {
+      const unsigned t32 = (unsigned)tile;  // (the host launches this kernel only for < 2^31 tiles)
+      const unsigned rest = t32 / (unsigned)M;
+      lv->t_m = (int)(t32 - rest * (unsigned)M);
+      int patch = (int)(rest / (unsigned)N);
+      lv->t_b = (int)(rest - (unsigned)patch * (unsigned)N);
+      int tl = 0, npx = 1;
+      for (; tl < L; ++tl) {
+        npx = (lv->W[tl] + TX - 1) >> Cfg::TXS;
+        const int np = ((lv->H[tl] + TY - 1) >> Cfg::TYS) * npx;
+        if (patch < np) break;
+        patch -= np;
+      }
+      const int prow = patch / npx;
+      lv->t_level = tl;
+      lv->t_y = prow << Cfg::TYS;
+      lv->t_x = (patch - prow * npx) << Cfg::TXS;
     }
-    const int prow = patch / npx;
-    const int y_base = prow << Cfg::TYS, x_base = (patch - prow * npx) << Cfg::TXS;
     if (threadIdx.x < MSDA_WIN_LEVELS) {
       lv->xmin[threadIdx.x] = 0x7fffffff; lv->ymin[threadIdx.x] = 0x7fffffff;
       lv->xmax[threadIdx.x] = -1; lv->ymax[threadIdx.x] = -1;
     }
     __syncthreads();
+    const int m = lv->t_m, b = lv->t_b;
+    const int tH = lv->H[lv->t_level], tW = lv->W[lv->t_level], tfirst = lv->first[lv->t_level];
+    const int y_base = lv->t_y, x_base = lv->t_x;
 
     // ---- A: geometry of my samples (two pairs of queries per warp) ----
     int xy[2];         // x0 | y0 << 16 of the 2x2 window, or -1: no contribution (outside sample / idle lane / no such query)
@@ -190,18 +197,18 @@ msda_fwd_win_kernel(const float* __restrict__ value, const int32_t* __restrict__
     }
     __syncthreads();
     {
-      const float* vimg = value + (long long)b * S * MD + m * D;
+      const char* vimg = reinterpret_cast<const char*>(value + (long long)b * S * MD + m * D) + (threadIdx.x & (LPR - 1)) * 16;
       for (int l = 0; l < L; ++l) {
         const int rows = lv->rows[l];
         if (rows == 0) continue;
-        const int ww = lv->ww[l], x0 = lv->xmin[l], y0 = lv->ymin[l], Wl = lv->W[l], stl = lv->st[l];
+        const int ww = lv->ww[l], Wl = lv->W[l];
+        const int pix0 = lv->st[l] + lv->ymin[l] * Wl + lv->xmin[l];        // first pixel of the box
         const unsigned magic = (unsigned)(0xffffffffu / (unsigned)ww) + 1u;  // exact r / ww for r * ww < 2^32
         const unsigned dst0 = win_s + (unsigned)lv->wbase[l] * Cfg::ROWB + (unsigned)(threadIdx.x & (LPR - 1)) * 16u;
+        const unsigned rowb = (unsigned)MD * 4u;                             // bytes between pixels (32-bit: S*M*D*4 <= 2^29)
         for (int r = threadIdx.x / LPR; r < rows; r += Cfg::THREADS / LPR) {
           const int ry = (int)__umulhi((unsigned)r, magic);
-          const int rx = r - ry * ww;
-          const float* src = vimg + (long long)(stl + (y0 + ry) * Wl + (x0 + rx)) * MD + (threadIdx.x & (LPR - 1)) * VEC;
-          win_cp_async16(dst0 + (unsigned)r * Cfg::ROWB, src);
+          win_cp_async16(dst0 + (unsigned)r * Cfg::ROWB, vimg + (unsigned)(pix0 + ry * (Wl - ww) + r) * rowb);
         }
       }
       win_cp_async_wait();
@@ -210,8 +217,9 @@ msda_fwd_win_kernel(const float* __restrict__ value, const int32_t* __restrict__
 
     // ---- C: the gather rounds, out of the windows ----
     const char* vbc = reinterpret_cast<const char*>(value + (long long)b * S * MD + (m * D + cl * VEC));
+    const unsigned base_s = win_s + (unsigned)cl * 16u;
     const size_t mdb = (size_t)MD * sizeof(T);
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       if (narrow) {  // a level narrower than 2 pixels has no regular 2x2 window: the flagged path does these units
         for (int k = 0; k < 2; ++k) {
@@ -250,16 +258,15 @@ msda_fwd_win_kernel(const float* __restrict__ value, const int32_t* __restrict__
           const uint4 ra = rec_a[src];
           const float2 rb = rec_b[src];
           uint4 v0, v1, v2, v3;
-          const bool glob = (ra.y & 0x80000000u) != 0;
-          if (!__any_sync(0xffffffffu, glob)) {
-            const unsigned a0 = win_s + ra.x + (unsigned)cl * 16u, a1 = a0 + ra.y;
+          if (!__any_sync(0xffffffffu, (int)ra.y < 0)) {  // the common round: every row of it is in a window
+            const unsigned a0 = base_s + ra.x, a1 = a0 + ra.y;
             v0 = lds128(a0); v1 = lds128(a0 + Cfg::ROWB); v2 = lds128(a1); v3 = lds128(a1 + Cfg::ROWB);
-          } else if (glob) {
+          } else if ((int)ra.y < 0) {                      // my sample's level is not staged: global tap rows
             const char* t0 = vbc + ra.x;
             const char* t1 = t0 + (ra.y & 0x7fffffffu);
             v0 = ldg128(t0); v1 = ldg128(t0 + mdb); v2 = ldg128(t1); v3 = ldg128(t1 + mdb);
           } else {
-            const unsigned a0 = win_s + ra.x + (unsigned)cl * 16u, a1 = a0 + ra.y;
+            const unsigned a0 = base_s + ra.x, a1 = a0 + ra.y;
             v0 = lds128(a0); v1 = lds128(a0 + Cfg::ROWB); v2 = lds128(a1); v3 = lds128(a1 + Cfg::ROWB);
           }
           const float wq[4] = {__uint_as_float(ra.z), __uint_as_float(ra.w), rb.x, rb.y};
