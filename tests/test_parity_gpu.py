@@ -127,6 +127,37 @@ def test_16bit_vs_oracle(w, dtype, cuda_device):
     assert_close(got[3], want[3], 1e-2, 1e-2 * rms(want[3]), "grad_attn")
 
 
+def _random_workloads(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 6))
+        levels = tuple((int(rng.integers(1, 23)), int(rng.integers(1, 23))) for _ in range(L))
+        D = int(rng.choice([1, 3, 8, 16, 24, 32, 32, 32, 40, 64, 96, 128]))
+        M = int(rng.choice([1, 2, 3, 5, 8, 8]))
+        P = int(rng.choice([1, 2, 3, 4, 4, 7, 9]))
+        out.append(Workload(f"rnd{i}_L{L}_M{M}_P{P}_D{D}", int(rng.integers(1, 4)), levels, int(rng.integers(1, 70)), M=M, P=P, D=D))
+    return out
+
+
+@pytest.mark.parametrize("w", _random_workloads(48, 20261017), ids=lambda w: w.name)
+def test_random_shapes_vs_oracle(w, cuda_device):
+    """Shape fuzz: random pyramids (levels down to 1 x 1), head / point / channel counts on and off the vector kernels' grid,
+    out-of-range locations -- fp32 forward and all three gradients against the fp64 oracle; bf16 forward where it applies."""
+    import zlib
+    x = torch_inputs(w, seed=zlib.crc32(w.name.encode()) % 1000, loc_mode="wide")
+    got = run_op(x, cuda_device)
+    want = oracle64(x)
+    assert_close(got[0], want[0], 1e-4, 1e-7 * max(rms(want[0]), 1e-30), "out")
+    check_grad_value(got[1], {"grad_value": want[1]}, 1e-4)
+    assert_close_grad_loc(got[2], want[2], x["loc"].numpy(), x["shapes"].numpy(), 1e-4)
+    assert_close_grad(got[3], want[3], 1e-4, "grad_attn")
+    xr = {k: (v.bfloat16().float() if v.is_floating_point() else v) for k, v in x.items()}
+    got16 = run_op(xr, cuda_device, dtype=torch.bfloat16, need_grad=False)
+    want16 = oracle64(xr)
+    assert_close(got16[0], want16[0], 1e-2, 1e-2 * max(rms(want16[0]), 1e-30), "out (bf16)")
+
+
 @pytest.mark.parametrize("which", ["loc", "attn", "both"])
 @pytest.mark.parametrize("dtype", [torch.bfloat16, torch.float16], ids=["bf16", "f16"])
 @pytest.mark.parametrize("w", SHAPES[:6], ids=lambda w: w.name)
