@@ -232,3 +232,58 @@ def test_unfused_module_under_autocast_keeps_fp32_locations(dtype, cuda_device):
         # (gradients through the piecewise-constant bilinear derivative: see tests/test_ref_module_autocast_gpu.py)
         assert e_g < (5e-2 if name == "out" else 4e-1) * scale, (name, e_g, scale)
         assert e_g < 2.0 * e_f + 1e-3 * scale, (name, e_g, e_f)
+
+
+def _fused_fuzz_cases(n, seed):
+    rng = np.random.default_rng(seed)
+    out = []
+    for i in range(n):
+        L = int(rng.integers(1, 5))
+        P = int(rng.choice([1, 2, 3, 4, 4, 8]))
+        while L * P > 32:
+            P //= 2
+        levels = tuple((int(rng.integers(2, 31)), int(rng.integers(2, 31))) for _ in range(L))
+        out.append((i, int(rng.integers(1, 4)), levels, int(rng.integers(1, 90)), int(rng.choice([1, 2, 5, 8, 8])), P,
+                    int(rng.choice([16, 32, 32, 64, 128])), int(rng.choice([2, 4]))))
+    return out
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("case", _fused_fuzz_cases(32, 7), ids=lambda c: "fz%d_N%d_L%d_Lq%d_M%d_P%d_D%d_rd%d" % (c[0], c[1], len(c[2]), c[3], c[4], c[5], c[6], c[7]))
+def test_fused_function_fuzz_against_the_unfused_composition(case, cuda_device):
+    """Shape fuzz of the fused operator (softmax + location arithmetic inside the kernels, both reference-point forms) against
+    eager softmax / location arithmetic + the plain operator: forward and the four gradients, fp32."""
+    msda.load_ops()
+    _, N, levels, Lq, M, P, D, ref_dim = case
+    dev = cuda_device
+    g = torch.Generator(device=dev).manual_seed(100 + case[0])
+    L = len(levels)
+    S = sum(h * w for h, w in levels)
+    shapes = torch.tensor(levels, dtype=torch.int32, device=dev)
+    start = torch.cat((shapes.new_zeros((1,)), (shapes[:, 0] * shapes[:, 1]).cumsum(0)[:-1])).to(torch.int32)
+    rnd = lambda *s: torch.rand(*s, device=dev, generator=g)
+    value = rnd(N, S, M, D) - 0.5
+    ref = rnd(N, Lq, L, 2) * 1.2 - 0.1
+    if ref_dim == 4:
+        ref = torch.cat([ref, rnd(N, Lq, L, 2) * 0.3], -1)
+    off = (rnd(N, Lq, M, L, P, 2) - 0.5) * 8
+    logits = (rnd(N, Lq, M, L * P) - 0.5) * 4
+    go = rnd(N, Lq, M * D) - 0.5
+    if not msda.fused_supported(value, shapes, ref, off, logits):
+        pytest.skip("shape outside the fused kernels")
+    v1, r1, o1, l1 = [t.detach().clone().requires_grad_(True) for t in (value, ref, off, logits)]
+    out1 = msda.MSDeformAttnFusedFunction.apply(v1, shapes, start, r1, o1, l1)
+    out1.backward(go)
+    v2, r2, o2, l2 = [t.detach().clone().requires_grad_(True) for t in (value, ref, off, logits)]
+    attn = torch.softmax(l2, -1).view(N, Lq, M, L, P)
+    if ref_dim == 2:
+        norm = torch.stack([shapes[..., 1], shapes[..., 0]], -1)
+        loc = r2[:, :, None, :, None, :] + o2 / norm[None, None, None, :, None, :]
+    else:
+        loc = r2[:, :, None, :, None, :2] + o2 / P * r2[:, :, None, :, None, 2:] * 0.5
+    out2 = msda.MSDeformAttnFunction.apply(v2, shapes, start, loc.contiguous(), attn.contiguous(), 64)
+    out2.backward(go)
+    f = lambda t: t.detach().double().cpu().numpy()
+    assert_close(f(out1), f(out2), 1e-4, 1e-4 * rms(f(out2)), "out")
+    for a, b, n in ((v1, v2, "grad_value"), (r1, r2, "grad_ref"), (o1, o2, "grad_offsets"), (l1, l2, "grad_logits")):
+        assert_close(f(a.grad), f(b.grad), 1e-4, 2e-4 * max(rms(f(b.grad)), 1e-30), n)
