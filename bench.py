@@ -407,6 +407,9 @@ def main():
         extra = run_extra(torch, msda, _capi, dev, tdt, elt, peak)
     # BASELINE.json's target is quoted on the 800x1333 pyramid with 300 queries: its forward is timed in every run (rank 0)
     north_star = north_star_forward(torch, msda, dev, tdt, elt, peak) if rank == 0 and not args.no_north_star else None
+    # ... and configs[3] itself, B = 32 images batch-sharded over the ranks (strong scaling): the operator census of one
+    # DeformableDETR-R50 inference forward, every rank takes part (max over ranks)
+    census = north_star_census(torch, msda, dist, dev, tdt, world, rank) if not args.no_north_star else None
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -441,6 +444,8 @@ def main():
         }
         if north_star:
             line["north_star_forward"] = north_star
+        if census:
+            line["north_star_census_b32"] = census
         if extra:
             line["extra"] = extra
         emit(line)
@@ -633,6 +638,56 @@ def north_star_forward(torch, msda, dev, tdt, elt, peak):
         del g, sets
         torch.cuda.empty_cache()
     return res
+
+
+def north_star_census(torch, msda, dist, dev, tdt, world, rank, global_batch=32):
+    """BASELINE.json configs[3] as far as this path goes: the 12 operator calls of one DeformableDETR-R50 inference forward
+    -- 6 encoder calls (Lq = S = 22 223) + 6 decoder calls (Lq = 300) on the 800x1333 pyramid -- for a GLOBAL batch of 32
+    images split over the ranks (strong scaling, no collective on the data path).  Each call has its own input set (a
+    layer's value tensor is new), one CUDA graph of the 12 forwards, median of 5 replays, max over ranks."""
+    from aloception_oss_b200.synthetic import WORKLOADS, device_inputs
+
+    n_local = global_batch // world + (1 if rank < global_batch % world else 0)
+    if n_local == 0:
+        return None
+    calls = []
+    for name, mode, n_sets in (("C4ENC", "raster", 3), ("C4DEC", "unit", 3)):
+        w = WORKLOADS[name].with_batch(n_local)
+        sets = [device_inputs(w, seed=900 + 10 * rank + i, device=dev, dtype=tdt, loc_mode=mode) for i in range(n_sets)]
+        for s_ in sets:
+            s_["out"] = torch.empty((w.N, w.Lq, w.M * w.D), dtype=tdt, device=dev)
+        calls += [sets[i % n_sets] for i in range(6)]
+    fn = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], out=s["out"])
+    for s_ in calls[:2] + calls[6:8]:
+        fn(s_)
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        for s_ in calls:
+            fn(s_)
+    g.replay()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    t = torch.tensor([statistics.median(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del g, calls
+    torch.cuda.empty_cache()
+    samples = global_batch * (22223 + 300) * 8 * 16 * 6
+    return {"workload": "configs[3]: 6 encoder (Lq = S = 22223) + 6 decoder (Lq = 300) forward calls, 800x1333 pyramid, "
+                        "global batch 32 split over the ranks", "global_batch": global_batch, "images_per_gpu": n_local,
+            "ms_per_forward_census": round(ms, 3), "gsamples_per_s": round(samples / (ms * 1e-3) / 1e9, 2),
+            "scaling": "strong", "timing": "one CUDA graph of the 12 calls, median of 5 replays, max over ranks"}
 
 
 def run_extra(torch, msda, _capi, dev, tdt, elt, peak):

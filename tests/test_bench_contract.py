@@ -83,3 +83,16 @@ def test_touched_bytes_counts_rows_where_taps_land():
     nqmlp, nqmd, nsmd = 1 * 1 * 2 * 2 * 1, 1 * 1 * 2 * 8, 1 * 20 * 2 * 8
     assert tb["fwd"] == 4 * (9 * 8 + 3 * nqmlp + nqmd) + 12 * 2
     assert tb["bwd"] == 4 * (9 * 8 + nsmd + 6 * nqmlp + nqmd) + 12 * 2
+
+
+def test_north_star_census_splits_the_global_batch_over_the_ranks():
+    """north_star_census_b32: 32 images over `world` ranks, remainder to the first ranks; a rank without images reports nothing."""
+    import inspect
+
+    bench = _load_bench()
+    src = inspect.getsource(bench.north_star_census)
+    assert "global_batch // world + (1 if rank < global_batch % world else 0)" in src
+    for world in (1, 2, 3, 4, 8, 40):
+        per = [32 // world + (1 if r < 32 % world else 0) for r in range(world)]
+        assert sum(per) == 32 and max(per) - min(per) <= 1
+    assert bench.north_star_census(None, None, None, None, None, 40, 39) is None  # rank 39 of 40 has no image
