@@ -410,6 +410,7 @@ def main():
     # ... and configs[3] itself, B = 32 images batch-sharded over the ranks (strong scaling): the operator census of one
     # DeformableDETR-R50 inference forward, every rank takes part (max over ranks)
     census = north_star_census(torch, msda, dist, dev, tdt, world, rank) if not args.no_north_star else None
+    census_train = training_census(torch, msda, dist, dev, tdt, world) if not args.no_north_star else None
 
     cpu_base = None
     if rank == 0 and not args.no_cpu_baseline:
@@ -446,6 +447,8 @@ def main():
             line["north_star_forward"] = north_star
         if census:
             line["north_star_census_b32"] = census
+        if census_train:
+            line["training_census_b2_per_gpu"] = census_train
         if extra:
             line["extra"] = extra
         emit(line)
@@ -688,6 +691,59 @@ def north_star_census(torch, msda, dist, dev, tdt, world, rank, global_batch=32)
                         "global batch 32 split over the ranks", "global_batch": global_batch, "images_per_gpu": n_local,
             "ms_per_forward_census": round(ms, 3), "gsamples_per_s": round(samples / (ms * 1e-3) / 1e9, 2),
             "scaling": "strong", "timing": "one CUDA graph of the 12 calls, median of 5 replays, max over ranks"}
+
+
+def training_census(torch, msda, dist, dev, tdt, world, per_gpu_batch=2):
+    """BASELINE.json configs[4] as far as this path goes: the 12 forward + 12 backward operator calls of one DeformableDETR-R50
+    training step at 2 images per GPU (weak scaling: every rank does the same work), 800x1333 pyramid.  One CUDA graph of the 24
+    calls (each layer its own inputs and result buffers), median of 5 replays, max over ranks."""
+    from aloception_oss_b200.synthetic import WORKLOADS, device_inputs
+
+    calls = []
+    for name, mode, n_sets in (("C5ENC", "raster", 6), ("C5DEC", "unit", 6)):
+        w = WORKLOADS[name].with_batch(per_gpu_batch)
+        for i in range(n_sets):
+            s_ = device_inputs(w, seed=700 + i, device=dev, dtype=tdt, loc_mode=mode)
+            s_["out"] = torch.empty((w.N, w.Lq, w.M * w.D), dtype=tdt, device=dev)
+            s_["grads"] = [torch.empty_like(s_["value"]), torch.empty_like(s_["loc"]), torch.empty_like(s_["attn"])]
+            calls.append(s_)
+    fwd = lambda s: msda.ms_deform_attn_forward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], out=s["out"])
+    bwd = lambda s: msda.ms_deform_attn_backward(s["value"], s["shapes"], s["start"], s["loc"], s["attn"], s["grad_out"], grads=s["grads"])
+
+    def step():
+        for s_ in calls:
+            fwd(s_)
+        for s_ in reversed(calls):
+            bwd(s_)
+
+    step()
+    torch.cuda.synchronize()
+    g = torch.cuda.CUDAGraph()
+    with torch.cuda.graph(g):
+        step()
+    g.replay()
+    torch.cuda.synchronize()
+    times = []
+    for _ in range(5):
+        if world > 1:
+            dist.barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        g.replay()
+        e1.record()
+        torch.cuda.synchronize()
+        times.append(e0.elapsed_time(e1))
+    t = torch.tensor([statistics.median(times)], device=dev, dtype=torch.float64)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item())
+    del g, calls
+    torch.cuda.empty_cache()
+    samples = per_gpu_batch * world * (22223 + 300) * 8 * 16 * 6
+    return {"workload": "configs[4]: 12 forward + 12 backward operator calls of one training step, 800x1333 pyramid, "
+                        "2 images per GPU", "images_per_gpu": per_gpu_batch, "global_batch": per_gpu_batch * world,
+            "ms_per_step_census": round(ms, 3), "gsamples_per_s_fwd_bwd": round(samples / (ms * 1e-3) / 1e9, 2),
+            "scaling": "weak", "timing": "one CUDA graph of the 24 calls, median of 5 replays, max over ranks"}
 
 
 def run_extra(torch, msda, _capi, dev, tdt, elt, peak):
