@@ -12,8 +12,13 @@
 // is not staged: its samples keep their global tap addresses and are gathered as in the unit-ordered kernel, round by round.
 // Pure re-scheduling: per unit the FMAs run in the order of msda_fwd_unit's speculative path with the same weights, so the result
 // is bit-identical as long as every loaded value is finite; a unit whose sums are not finite is redone on the flagged path.
-// One warp serves two heads?  No: one warp serves UPW = 4 queries of the tile, two at a time (lanes 0..15: the samples of one
-// query, lanes 16..31 those of the next; needs L * P <= 16), like msda_fwd_pair.
+// One warp serves UPW = 4 queries of the tile, two at a time (lanes 0..15: the samples of one query, lanes 16..31 those of the
+// next; needs L * P <= 16), like msda_fwd_pair.
+//
+// MEASURED (B200, ENC = N 2, 100^2 pyramid, Lq = S, fp32; profiles/r2_ncu_enc_fwd_paired.md): bit-identical, L2 throughput 53 -> 18 %
+// of peak, 165 us against 95 us for the unit-ordered kernel (187 us with non-local locations).  Phase isolation: tile loop +
+// barriers 29 us, + geometry / boxes 68 us, + copy 87 us, and the shared-memory gather rounds add 80 us by themselves (72 LDS
+// wavefronts per unit = 53 us at the pipe's peak).  Opt-in (knob "fwd_win_mode" = 2), not selected automatically.
 #pragma once
 #include "msda_kernels.cuh"
 
