@@ -104,6 +104,73 @@ int main(void) {
   CK(cudaStreamSynchronize(st));
   ok &= close_enough("plugin_twin", g_out, w_out, n_out);
 
+  /* deterministic backward: 64-bit fixed-point accumulation in caller-provided scratch, twice -> the same bits */
+  {
+    const size_t ws_bytes = msda_backward_workspace_bytes_ex(&dims, MSDA_F32, MSDA_BWD_DETERMINISTIC);
+    void* d_ws = NULL;
+    float* g_gv2 = malloc(4 * n_value);
+    CK(cudaMalloc(&d_ws, ws_bytes));
+    for (int rep = 0; rep < 2; ++rep) {
+      if (msda_backward(d_go, d_value, d_shapes, d_start, d_loc, d_attn, d_gv, d_gl, d_ga, d_ws, ws_bytes, &dims, MSDA_F32,
+                        MSDA_BWD_DETERMINISTIC, st)) { fprintf(stderr, "%s\n", msda_last_error_string()); return 1; }
+      CK(cudaMemcpyAsync(rep ? g_gv2 : g_gv, d_gv, 4 * n_value, cudaMemcpyDeviceToHost, st));
+    }
+    CK(cudaStreamSynchronize(st));
+    ok &= close_enough("grad_value (deterministic)", g_gv, w_gv, n_value);
+    if (memcmp(g_gv, g_gv2, 4 * n_value)) { fprintf(stderr, "deterministic backward is not bit-reproducible\n"); ok = 0; }
+    CK(cudaFree(d_ws));
+    free(g_gv2);
+  }
+
+  /* forward with caller-provided scratch: no schedule needs it by default (0 bytes); the opt-in SM-affine paired forward does */
+  {
+    if (msda_forward_workspace_bytes(&dims, MSDA_F32) != 0) { fprintf(stderr, "default forward asks for scratch\n"); ok = 0; }
+    msda_set_tuning("fwd_pair_mode", 3);
+    const size_t ws_bytes = msda_forward_workspace_bytes(&dims, MSDA_F32);
+    void* d_ws = NULL;
+    if (ws_bytes == 0) { fprintf(stderr, "fwd_pair_mode = 3 asks for no scratch\n"); ok = 0; }
+    CK(cudaMalloc(&d_ws, ws_bytes ? ws_bytes : 8));
+    CK(cudaMemsetAsync(d_out, 0xff, 4 * n_out, st));
+    if (msda_forward_ws(d_value, d_shapes, d_start, d_loc, d_attn, d_out, d_ws, ws_bytes, &dims, MSDA_F32, st)) { fprintf(stderr, "%s\n", msda_last_error_string()); return 1; }
+    CK(cudaMemcpyAsync(g_out, d_out, 4 * n_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    ok &= close_enough("forward_ws (paired, SM-affine)", g_out, w_out, n_out);
+    msda_set_tuning("fwd_pair_mode", 0);
+    CK(cudaFree(d_ws));
+  }
+
+  /* mixed precision: bf16 value / output next to fp32 locations and weights (MSDA_LOC_F32 | MSDA_ATTN_F32) */
+  {
+    uint16_t* h16 = malloc(2 * n_value);
+    float* vr = malloc(4 * n_value);
+    for (size_t i = 0; i < n_value; ++i) {  /* round to nearest even, keep the rounded value for the oracle */
+      uint32_t u; memcpy(&u, &value[i], 4);
+      u += 0x7fffu + ((u >> 16) & 1u);
+      h16[i] = (uint16_t)(u >> 16);
+      u &= 0xffff0000u; memcpy(&vr[i], &u, 4);
+    }
+    float* w16 = malloc(4 * n_out);
+    msda_oracle_forward_f32(vr, shapes, start, loc, attn, w16, N, S, M, D, L, Lq, P);
+    uint16_t *d_v16, *d_o16, *o16 = malloc(2 * n_out);
+    CK(cudaMalloc((void**)&d_v16, 2 * n_value)); CK(cudaMalloc((void**)&d_o16, 2 * n_out));
+    CK(cudaMemcpyAsync(d_v16, h16, 2 * n_value, cudaMemcpyHostToDevice, st));
+    if (msda_forward(d_v16, d_shapes, d_start, d_loc, d_attn, d_o16, &dims, MSDA_BF16 | MSDA_LOC_F32 | MSDA_ATTN_F32, st)) { fprintf(stderr, "%s\n", msda_last_error_string()); return 1; }
+    CK(cudaMemcpyAsync(o16, d_o16, 2 * n_out, cudaMemcpyDeviceToHost, st));
+    CK(cudaStreamSynchronize(st));
+    double worst = 0.0, scale = 0.0;
+    for (size_t i = 0; i < n_out; ++i) {
+      uint32_t u = (uint32_t)o16[i] << 16; float f; memcpy(&f, &u, 4);
+      const double e = fabs((double)f - w16[i]);
+      if (e > worst) worst = e;
+      if (fabs(w16[i]) > scale) scale = fabs(w16[i]);
+    }
+    if (!(worst <= 1e-2 * scale)) { fprintf(stderr, "mixed-precision forward: max error %g vs scale %g\n", worst, scale); ok = 0; }
+    else printf("forward (bf16 value, fp32 loc / attn): max |err| %.3g (output scale %.3g)\n", worst, scale);
+    if (msda_forward(d_v16, d_shapes, d_start, d_loc, d_attn, d_o16, &dims, MSDA_F64 | MSDA_LOC_F32, st) == 0) { fprintf(stderr, "MSDA_F64 | MSDA_LOC_F32 was not rejected\n"); ok = 0; }
+    CK(cudaFree(d_v16)); CK(cudaFree(d_o16));
+    free(h16); free(vr); free(w16); free(o16);
+  }
+
   /* error path: bad dtype is reported, not crashed on */
   if (msda_forward(d_value, d_shapes, d_start, d_loc, d_attn, d_out, &dims, 42, st) == 0 || !strstr(msda_last_error_string(), "dtype")) {
     fprintf(stderr, "bad dtype was not rejected\n");

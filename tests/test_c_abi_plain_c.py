@@ -45,6 +45,9 @@ def test_plain_c_program_matches_the_oracle(tmp_path, cuda_device):
     assert "C ABI smoke: OK" in res.stdout
     for name in ("forward", "grad_value", "grad_attn", "grad_loc", "forward_host", "plugin_twin"):
         assert f"{name:<12s} ok" in res.stdout, res.stdout
+    # deterministic backward (bit-reproducible), msda_forward_ws with the opt-in SM-affine schedule, bf16 value + fp32 loc / attn
+    assert "grad_value (deterministic)" in res.stdout and "forward_ws (paired, SM-affine)" in res.stdout, res.stdout
+    assert "forward (bf16 value, fp32 loc / attn): max |err|" in res.stdout, res.stdout
 
 
 # ------------------------------------------------------------------ include/sortv_b200.h
