@@ -804,3 +804,54 @@ def test_module_under_torch_compile_matches_eager(cuda_device):
         pytest.xfail(f"torch.compile could not trace the module here: {type(e).__name__}: {str(e)[:200]}")
     assert torch.allclose(got, want, rtol=1e-4, atol=1e-5)
     assert torch.allclose(cq, gq, rtol=1e-4, atol=1e-5) and torch.allclose(cs, gs, rtol=1e-4, atol=1e-5)
+
+
+def test_concurrent_streams_and_threads(cuda_device):
+    """The library keeps per-call state (mixed-precision bits, scratch pointer, pre-zeroed flag) in thread-local variables and
+    nothing per stream: two Python threads, each on its own CUDA stream, one calling the fp32 operator and the other the
+    mixed-precision (bf16 value, fp32 locations) one with the opt-in SM-affine schedule, must both get their single-threaded
+    results."""
+    import threading
+
+    dev = cuda_device
+    w = Workload("mt", 2, ((24, 31), (12, 16), (6, 8), (3, 4)), 1068, M=8, P=4, D=32)
+    x = torch_inputs(w, seed=77, loc_mode="wide")
+    shapes, start = x["shapes"].to(dev), x["start"].to(dev)
+    v32, loc, attn, go = x["value"].to(dev), x["loc"].to(dev), x["attn"].to(dev), x["grad_out"].to(dev)
+    v16, go16 = v32.bfloat16(), go.bfloat16()
+    want32 = msda.ms_deform_attn_forward(v32, shapes, start, loc, attn)
+    want16 = msda.ms_deform_attn_forward(v16, shapes, start, loc, attn)
+    wantb = msda.ms_deform_attn_backward(v16, shapes, start, loc, attn, go16)
+    torch.cuda.synchronize()
+    errors = []
+
+    def worker(kind):
+        try:
+            stream = torch.cuda.Stream(device=dev)
+            with torch.cuda.stream(stream):
+                for _ in range(40):
+                    if kind == 0:
+                        got = msda.ms_deform_attn_forward(v32, shapes, start, loc, attn)
+                        ok = torch.equal(got, want32)
+                    else:
+                        got = msda.ms_deform_attn_forward(v16, shapes, start, loc, attn)
+                        gb = msda.ms_deform_attn_backward(v16, shapes, start, loc, attn, go16)
+                        ok = torch.equal(got, want16) and torch.equal(gb[1], wantb[1]) and gb[1].dtype == torch.float32
+                    stream.synchronize()
+                    if not ok:
+                        errors.append(kind)
+                        return
+        except Exception as e:  # noqa: BLE001
+            errors.append(repr(e))
+
+    _capi.set_tuning("fwd_pair_mode", 3)
+    try:
+        ts = [threading.Thread(target=worker, args=(k,)) for k in (0, 1, 0, 1)]
+        for t in ts:
+            t.start()
+        for t in ts:
+            t.join()
+    finally:
+        _capi.set_tuning("fwd_pair_mode", 0)
+    torch.cuda.synchronize()
+    assert not errors, errors
